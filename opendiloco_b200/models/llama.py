@@ -1,0 +1,483 @@
+"""Llama causal LM on the flat arena: hand-scheduled forward/backward over sm_100a kernels.
+
+There is no autograd graph on the hot path.  ``LlamaEngine`` runs the layer program explicitly
+(K1..K8 of SURVEY.md §2.5), keeps activations in shape-keyed static workspaces (CUDA-graph friendly) and
+accumulates weight gradients straight into the fp32 gradient arena.  ``LlamaForCausalLM`` is the user-facing
+``nn.Module``: HF-compatible parameter names / state dict / ``forward(input_ids, labels) -> .loss`` whose
+``.backward()`` triggers the engine's backward through a single autograd node, so reference-style training loops
+(train_fsdp.py:378-383, train_diloco_torch.py:312-318) run unchanged.
+
+Op semantics follow the installed HF implementation the reference delegates to:
+RMSNorm modeling_llama.py:62-67, RoPE :117-168, attention :251-289, MLP :182-184, decoder layer :303-332,
+LM head + shifted CE :484-491 / loss_utils.py:45-67.
+"""
+from __future__ import annotations
+
+import json
+import os
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Any
+
+import torch
+from torch import nn
+
+from ..ops import attention as A
+from ..ops import gemm as G
+from ..ops import kernels as K
+from .arena import ParamArena, hf_param_order
+from .config import LlamaConfig
+
+IGNORE_INDEX = -100
+
+
+@dataclass
+class CausalLMOutput:
+    loss: torch.Tensor | None = None
+    logits: torch.Tensor | None = None
+
+    def __getitem__(self, k):
+        return getattr(self, k) if isinstance(k, str) else (self.loss, self.logits)[k]
+
+
+# ======================================================================================================= engine
+class _Workspace:
+    """Static activation buffers for one (B, S) shape."""
+
+    def __init__(self, cfg: LlamaConfig, B: int, S: int, device, dtype, lce_chunk: int):
+        T, h, i, L = B * S, cfg.hidden_size, cfg.intermediate_size, cfg.num_hidden_layers
+        e = lambda *shape, dt=dtype: torch.empty(*shape, dtype=dt, device=device)  # noqa: E731
+        f32 = torch.float32
+        self.B, self.S, self.T = B, S, T
+        self.ids = torch.empty(T, dtype=torch.int64, device=device)
+        self.labels = torch.empty(T, dtype=torch.int64, device=device)
+        # saved per layer
+        self.xa = [e(T, h) for _ in range(L)]         # residual stream entering the attention block
+        self.rstd1 = [e(T, dt=f32) for _ in range(L)]
+        self.xn1 = [e(T, h) for _ in range(L)]
+        self.qkv = [e(T, cfg.qkv_dim) for _ in range(L)]
+        self.att = [None] * L                          # attention output (+aux) allocated by the attention op
+        self.aux = [None] * L
+        self.xm = [e(T, h) for _ in range(L)]         # residual stream entering the MLP block
+        self.rstd2 = [e(T, dt=f32) for _ in range(L)]
+        self.xn2 = [e(T, h) for _ in range(L)]
+        self.gu = [e(T, 2 * i) for _ in range(L)]
+        self.act = [e(T, i) for _ in range(L)]
+        self.xf = e(T, h)                              # residual stream entering the final norm
+        self.rstdf = e(T, dt=f32)
+        self.xnf = e(T, h)
+        # transient
+        self.proj = e(T, h)                            # o-proj / down-proj output (the residual delta)
+        self.dx = e(T, h)                              # gradient of the residual stream
+        self.dn = e(T, h)                              # gradient w.r.t. a normed activation
+        self.datt = e(T, h)
+        self.dqkv = e(T, cfg.qkv_dim)
+        self.dact = e(T, i)
+        self.dxnf = e(T, h)
+        self.logits = e(min(lce_chunk, T), cfg.vocab_size)
+        self.loss_sum = torch.zeros(1, dtype=f32, device=device)
+        self.gscale = torch.ones(1, dtype=f32, device=device)
+        self.n_valid = torch.ones(1, dtype=f32, device=device)
+        self.sumsq = torch.zeros(1, dtype=f32, device=device)
+        self.cos, self.sin = K.rope_tables(S, cfg.head_dim, cfg.rope_theta, device)
+
+
+class LlamaEngine:
+    def __init__(self, cfg: LlamaConfig, arena: ParamArena, lce_chunk: int = 2048):
+        self.cfg, self.arena = cfg, arena
+        self.lce_chunk = lce_chunk
+        self._ws: dict[tuple, _Workspace] = {}
+        self.collect_act_norms = False
+        self.act_norms: dict[str, torch.Tensor] = {}
+        self.module_hooks: dict[str, Any] = {}     # name -> holder module with user forward hooks
+        self.head_grad_tmp: torch.Tensor | None = None
+
+    def workspace(self, B: int, S: int) -> _Workspace:
+        key = (B, S, str(self.arena.device), self.arena.compute_dtype)
+        ws = self._ws.get(key)
+        if ws is None:
+            if len(self._ws) >= 2:       # keep at most two shapes resident (train + eval)
+                self._ws.pop(next(iter(self._ws)))
+            ws = _Workspace(self.cfg, B, S, self.arena.device, self.arena.compute_dtype, self.lce_chunk)
+            self._ws[key] = ws
+        return ws
+
+    # --------------------------------------------------------------------------------------------- forward
+    def _fire_hooks(self, name: str, out: torch.Tensor) -> None:
+        mod = self.module_hooks.get(name)
+        if mod is not None and mod._forward_hooks:
+            for hook in list(mod._forward_hooks.values()):
+                hook(mod, (), out)
+
+    def forward_hidden(self, ws: _Workspace, ids: torch.Tensor, attention_mask: torch.Tensor | None = None) -> torch.Tensor:
+        cfg, ar = self.cfg, self.arena
+        B, S, L = ws.B, ws.S, cfg.num_hidden_layers
+        Hq, Hkv, D = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
+        ws.ids.copy_(ids.reshape(-1), non_blocking=True)
+        K.embedding_fwd(ws.ids, ar.w("model.embed_tokens.weight"), out=ws.xa[0])
+        delta = None
+        for l in range(L):
+            p = f"model.layers.{l}."
+            x_prev = ws.xa[l] if l == 0 else ws.xm[l - 1]
+            # --- attention block:  xa = x_prev + delta ; xn1 = norm(xa)
+            K.rmsnorm_fwd(x_prev, ar.w(p + "input_layernorm.weight"), cfg.rms_norm_eps, delta=delta, out=ws.xn1[l],
+                          rstd=ws.rstd1[l], x_out=ws.xa[l])
+            G.mm_nt(ws.xn1[l], ar.qkv_w(l), out=ws.qkv[l])
+            K.rope_(ws.qkv[l], ws.cos, ws.sin, S, Hq + Hkv, D)
+            if attention_mask is None:
+                ws.att[l], ws.aux[l] = A.attention_fwd(ws.qkv[l], B, S, Hq, Hkv, D)
+            else:
+                ws.att[l], ws.aux[l] = _masked_attention_fwd(ws.qkv[l], attention_mask, B, S, Hq, Hkv, D)
+            G.mm_nt(ws.att[l], ar.w(p + "self_attn.o_proj.weight"), out=ws.proj)
+            if self.collect_act_norms:
+                self.act_norms[f"activation/{p}self_attn"] = ws.proj.float().norm(p=2)
+            self._fire_hooks(p + "self_attn", ws.proj)
+            # --- MLP block:  xm = xa + proj ; xn2 = norm(xm)
+            K.rmsnorm_fwd(ws.xa[l], ar.w(p + "post_attention_layernorm.weight"), cfg.rms_norm_eps, delta=ws.proj,
+                          out=ws.xn2[l], rstd=ws.rstd2[l], x_out=ws.xm[l])
+            G.mm_nt(ws.xn2[l], ar.gu_w(l), out=ws.gu[l])
+            K.swiglu_fwd(ws.gu[l], out=ws.act[l])
+            G.mm_nt(ws.act[l], ar.w(p + "mlp.down_proj.weight"), out=ws.proj)
+            delta = ws.proj
+        K.rmsnorm_fwd(ws.xm[L - 1], ar.w("model.norm.weight"), cfg.rms_norm_eps, delta=delta, out=ws.xnf, rstd=ws.rstdf,
+                      x_out=ws.xf)
+        return ws.xnf
+
+    # --------------------------------------------------------------------------------------------- LM head + loss
+    def head_loss(self, ws: _Workspace, labels: torch.Tensor | None, loss_scale: float, with_grad: bool,
+                  direct: bool) -> torch.Tensor:
+        """Chunked linear-cross-entropy.  Returns the mean loss (0-dim fp32 tensor on device).
+
+        with_grad: also produce d(xnf) in ws.dxnf and the lm_head weight gradient, scaled by loss_scale / n_valid.
+        direct: accumulate the lm_head gradient into the arena now (scale known); otherwise into ``head_grad_tmp`` so
+        that autograd can apply the upstream gradient later.
+        """
+        cfg, ar = self.cfg, self.arena
+        T, V = ws.T, cfg.vocab_size
+        B, S = ws.B, ws.S
+        # HF shift: position s predicts token s+1 ; last position of every sequence is ignored
+        lab = ws.labels.view(B, S)
+        src = labels.reshape(B, S)
+        lab[:, : S - 1].copy_(src[:, 1:], non_blocking=True)
+        lab[:, S - 1].fill_(IGNORE_INDEX)
+        ws.n_valid.copy_((ws.labels != IGNORE_INDEX).sum().to(torch.float32).reshape(1))
+        ws.n_valid.clamp_(min=1.0)
+        torch.reciprocal(ws.n_valid, out=ws.gscale)
+        ws.gscale.mul_(float(loss_scale))
+        ws.loss_sum.zero_()
+        w_lm = ar.w("lm_head.weight")
+        hooked = self.module_hooks.get("lm_head")
+        want_norm = self.collect_act_norms or (hooked is not None and bool(hooked._forward_hooks))
+        if want_norm:
+            ws.sumsq.zero_()
+        if with_grad:
+            if direct:
+                g_lm = ar.g("lm_head.weight")
+            else:
+                if self.head_grad_tmp is None:
+                    self.head_grad_tmp = torch.zeros(V, cfg.hidden_size, dtype=torch.float32, device=ar.device)
+                else:
+                    self.head_grad_tmp.zero_()
+                g_lm = self.head_grad_tmp
+        C = ws.logits.shape[0]
+        for c0 in range(0, T, C):
+            c1 = min(T, c0 + C)
+            logits = ws.logits[: c1 - c0]
+            G.mm_nt(ws.xnf[c0:c1], w_lm, out=logits)
+            if with_grad:
+                K.ce_fwd_bwd_(logits, ws.labels[c0:c1], ws.gscale, ws.loss_sum, ws.sumsq if want_norm else None)
+                G.mm_nn(logits, w_lm, out=ws.dxnf[c0:c1])
+                G.mm_tn_acc(logits, ws.xnf[c0:c1], g_lm)
+            else:
+                if want_norm:
+                    ws.sumsq.add_(logits.float().pow(2).sum())
+                K.ce_fwd(logits, ws.labels[c0:c1], ws.loss_sum)
+        if want_norm:
+            nrm = ws.sumsq.sqrt()[0]
+            if self.collect_act_norms:
+                self.act_norms["activation/lm_head"] = nrm
+            if hooked is not None and hooked._forward_hooks:
+                self._fire_hooks("lm_head", _NormOnly(nrm))
+        return (ws.loss_sum / ws.n_valid)[0]
+
+    def logits(self, ws: _Workspace) -> torch.Tensor:
+        """Materialise full logits [T, V] (inference / debugging only)."""
+        return G.mm_nt(ws.xnf, self.arena.w("lm_head.weight"))
+
+    # --------------------------------------------------------------------------------------------- backward
+    def backward(self, ws: _Workspace, attention_mask: torch.Tensor | None = None) -> None:
+        """Back-propagate ws.dxnf (gradient w.r.t. the final-norm output) through the stack, accumulating into arena.grad."""
+        cfg, ar = self.cfg, self.arena
+        B, S, L = ws.B, ws.S, cfg.num_hidden_layers
+        Hq, Hkv, D = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
+        K.rmsnorm_bwd(ws.dxnf, ws.xf, ar.w("model.norm.weight"), ws.rstdf, None, ws.dx, ar.g("model.norm.weight"))
+        for l in reversed(range(L)):
+            p = f"model.layers.{l}."
+            # ---- MLP block (ws.dx is the gradient of x_out = xm + down(act))
+            G.mm_tn_acc(ws.dx, ws.act[l], ar.g(p + "mlp.down_proj.weight"))
+            G.mm_nn(ws.dx, ar.w(p + "mlp.down_proj.weight"), out=ws.dact)
+            K.swiglu_bwd(ws.dact, ws.gu[l], ws.gu[l])                      # in place: gu <- d(gu)
+            G.mm_tn_acc(ws.gu[l], ws.xn2[l], ar.gu_g(l))
+            G.mm_nn(ws.gu[l], ar.gu_w(l), out=ws.dn)
+            K.rmsnorm_bwd(ws.dn, ws.xm[l], ar.w(p + "post_attention_layernorm.weight"), ws.rstd2[l], ws.dx, ws.dx,
+                          ar.g(p + "post_attention_layernorm.weight"))
+            # ---- attention block (ws.dx is now the gradient of xm = xa + o(att))
+            G.mm_tn_acc(ws.dx, ws.att[l], ar.g(p + "self_attn.o_proj.weight"))
+            G.mm_nn(ws.dx, ar.w(p + "self_attn.o_proj.weight"), out=ws.datt)
+            if attention_mask is None:
+                A.attention_bwd(ws.datt, ws.qkv[l], ws.att[l], ws.aux[l], ws.dqkv, B, S, Hq, Hkv, D)
+            else:
+                _masked_attention_bwd(ws.datt, ws.aux[l], ws.dqkv, B, S, Hq, Hkv, D)
+            K.rope_(ws.dqkv, ws.cos, ws.sin, S, Hq + Hkv, D, backward=True)
+            G.mm_tn_acc(ws.dqkv, ws.xn1[l], ar.qkv_g(l))
+            G.mm_nn(ws.dqkv, ar.qkv_w(l), out=ws.dn)
+            K.rmsnorm_bwd(ws.dn, ws.xa[l], ar.w(p + "input_layernorm.weight"), ws.rstd1[l], ws.dx, ws.dx,
+                          ar.g(p + "input_layernorm.weight"))
+            ws.att[l] = None
+            ws.aux[l] = None
+        K.embedding_bwd(ws.ids, ws.dx, ar.g("model.embed_tokens.weight"))
+
+    # --------------------------------------------------------------------------------------------- fused entry
+    def forward_backward(self, ids: torch.Tensor, labels: torch.Tensor, loss_scale: float = 1.0,
+                         attention_mask: torch.Tensor | None = None) -> torch.Tensor:
+        """One micro-batch: forward, loss, backward; gradients (scaled by loss_scale) are ADDED to arena.grad.
+        Returns the mean token loss as a device scalar (no host sync)."""
+        B, S = ids.shape
+        ws = self.workspace(B, S)
+        mask = _normalize_mask(attention_mask)
+        with torch.no_grad():
+            self.forward_hidden(ws, ids, mask)
+            loss = self.head_loss(ws, labels, loss_scale, with_grad=True, direct=True)
+            self.backward(ws, mask)
+        return loss
+
+
+class _NormOnly:
+    """Stand-in handed to lm_head forward hooks: the logits are never materialised, only their L2 norm exists."""
+
+    def __init__(self, nrm: torch.Tensor):
+        self._nrm = nrm
+
+    def norm(self, p=2):
+        return self._nrm
+
+
+def _normalize_mask(attention_mask: torch.Tensor | None) -> torch.Tensor | None:
+    """None when the mask is absent or all ones (pure causal fast path)."""
+    if attention_mask is None:
+        return None
+    if bool(attention_mask.all()):
+        return None
+    return attention_mask.bool()
+
+
+def _masked_attention_fwd(qkv, mask, B, S, Hq, Hkv, D):
+    """Padding-mask path (real text with pad tokens): library SDPA with an explicit mask, differentiated by autograd."""
+    q, k, v = A.split_qkv(qkv, B, S, Hq, Hkv, D)
+    leaves = [t.detach().transpose(1, 2).requires_grad_(True) for t in (q, k, v)]
+    causal = torch.ones(S, S, dtype=torch.bool, device=qkv.device).tril()
+    full = causal[None, None] & mask[:, None, None, :].to(qkv.device)
+    # keep fully-masked rows finite (pad queries): let them see themselves
+    full = full | torch.eye(S, dtype=torch.bool, device=qkv.device)[None, None]
+    with torch.enable_grad():
+        o = torch.nn.functional.scaled_dot_product_attention(leaves[0], leaves[1], leaves[2], attn_mask=full,
+                                                             enable_gqa=(Hq != Hkv))
+        out = o.transpose(1, 2).reshape(B * S, Hq * D)
+    return out.detach(), (out, leaves)
+
+
+def _masked_attention_bwd(dout, aux, dqkv, B, S, Hq, Hkv, D):
+    out, leaves = aux
+    gq, gk, gv = torch.autograd.grad(out, leaves, dout)
+    dq, dk, dv = A.split_qkv(dqkv, B, S, Hq, Hkv, D)
+    dq.copy_(gq.transpose(1, 2))
+    dk.copy_(gk.transpose(1, 2))
+    dv.copy_(gv.transpose(1, 2))
+
+
+# ======================================================================================================= nn.Module facade
+class _Holder(nn.Module):
+    """Parameter holder: the math runs in LlamaEngine, this only gives the weight its HF name."""
+
+    def __init__(self, weight: nn.Parameter | None = None):
+        super().__init__()
+        if weight is not None:
+            self.weight = weight
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("sub-modules of opendiloco_b200.LlamaForCausalLM are parameter holders; call the top-level model")
+
+
+class _EngineLoss(torch.autograd.Function):
+    """Single autograd node bridging loss.backward() to the engine's hand-written backward."""
+
+    @staticmethod
+    def forward(ctx, anchor: torch.Tensor, model: "LlamaForCausalLM", ids, labels, mask):
+        eng = model.engine
+        B, S = ids.shape
+        ws = eng.workspace(B, S)
+        eng.forward_hidden(ws, ids, mask)
+        loss = eng.head_loss(ws, labels, 1.0, with_grad=True, direct=False)
+        ctx.model, ctx.ws, ctx.mask = model, ws, mask
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        eng, ws = ctx.model.engine, ctx.ws
+        with torch.no_grad():
+            g32 = g.to(torch.float32)
+            ws.dxnf.mul_(g32.to(ws.dxnf.dtype))
+            eng.arena.g("lm_head.weight").addcmul_(eng.head_grad_tmp, g32.expand_as(eng.head_grad_tmp))
+            eng.backward(ws, ctx.mask)
+        return None, None, None, None, None
+
+
+class LlamaForCausalLM(nn.Module):
+    """Drop-in for the HF class the reference trains (train_fsdp.py:171-174, train_diloco_torch.py:183)."""
+
+    def __init__(self, config: LlamaConfig, device=None, precision: str = "bf16-mixed", seed: int | None = None,
+                 init: bool = True, lce_chunk: int = 2048):
+        super().__init__()
+        self.config = config
+        self.precision = precision
+        compute = {"bf16-mixed": torch.bfloat16, "fp16-mixed": torch.float16, "32-true": torch.float32}[precision]
+        device = torch.device(device if device is not None else "cpu")
+        self.arena = ParamArena(config, device, compute)
+        self.engine = LlamaEngine(config, self.arena, lce_chunk=lce_chunk)
+        self._build_tree()
+        if init:
+            self.arena.init_weights(seed)
+
+    # ------------------------------------------------------------------ module tree with HF names
+    def _build_tree(self) -> None:
+        cfg, ar = self.config, self.arena
+
+        def P(name: str) -> nn.Parameter:
+            prm = nn.Parameter(ar.p(name), requires_grad=True)
+            prm.grad = ar.g(name)
+            prm._odb_name = name
+            return prm
+
+        self.model = _Holder()
+        self.model.embed_tokens = _Holder(P("model.embed_tokens.weight"))
+        layers = []
+        for l in range(cfg.num_hidden_layers):
+            p = f"model.layers.{l}."
+            layer = _Holder()
+            layer.self_attn = _Holder()
+            for n in ("q_proj", "k_proj", "v_proj", "o_proj"):
+                setattr(layer.self_attn, n, _Holder(P(p + f"self_attn.{n}.weight")))
+            layer.mlp = _Holder()
+            for n in ("gate_proj", "up_proj", "down_proj"):
+                setattr(layer.mlp, n, _Holder(P(p + f"mlp.{n}.weight")))
+            layer.input_layernorm = _Holder(P(p + "input_layernorm.weight"))
+            layer.post_attention_layernorm = _Holder(P(p + "post_attention_layernorm.weight"))
+            layers.append(layer)
+            self.engine.module_hooks[p + "self_attn"] = layer.self_attn
+        self.model.layers = nn.ModuleList(layers)
+        self.model.norm = _Holder(P("model.norm.weight"))
+        self.lm_head = _Holder(P("lm_head.weight"))
+        self.engine.module_hooks["lm_head"] = self.lm_head
+
+    def _rebind(self) -> None:
+        for _, prm in self.named_parameters():
+            prm.data = self.arena.p(prm._odb_name)
+            prm.grad = self.arena.g(prm._odb_name)
+
+    # ------------------------------------------------------------------ device / dtype management
+    def to(self, *args, **kwargs):
+        device = kwargs.get("device")
+        for a in args:
+            if isinstance(a, (str, torch.device, int)):
+                device = a
+            elif isinstance(a, torch.dtype):
+                raise TypeError("opendiloco_b200 models keep fp32 master weights; choose `precision=` at construction")
+        if device is not None:
+            device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+            if device.type == "cuda" and device.index is None:
+                device = torch.device("cuda", torch.cuda.current_device())
+            if device != self.arena.device:
+                self.arena.migrate(device)
+                self.engine._ws.clear()
+                self.engine.head_grad_tmp = None
+                self._rebind()
+        return self
+
+    def cuda(self, device=None):
+        return self.to(torch.device("cuda", device if device is not None else torch.cuda.current_device()))
+
+    def cpu(self):
+        return self.to("cpu")
+
+    @property
+    def device(self) -> torch.device:
+        return self.arena.device
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, input_ids: torch.Tensor, attention_mask: torch.Tensor | None = None,
+                labels: torch.Tensor | None = None, return_logits: bool = False, **_unused) -> CausalLMOutput:
+        eng = self.engine
+        if input_ids.device != self.arena.device:
+            input_ids = input_ids.to(self.arena.device, non_blocking=True)
+        if labels is not None and labels.device != self.arena.device:
+            labels = labels.to(self.arena.device, non_blocking=True)
+        mask = _normalize_mask(attention_mask)
+        B, S = input_ids.shape
+        if labels is not None and torch.is_grad_enabled() and self.training:
+            loss = _EngineLoss.apply(self.lm_head.weight, self, input_ids, labels, mask)
+            return CausalLMOutput(loss=loss)
+        with torch.no_grad():
+            ws = eng.workspace(B, S)
+            eng.forward_hidden(ws, input_ids, mask)
+            loss = eng.head_loss(ws, labels, 1.0, with_grad=False, direct=False).clone() if labels is not None else None
+            logits = eng.logits(ws).view(B, S, -1) if (return_logits or labels is None) else None
+        return CausalLMOutput(loss=loss, logits=logits)
+
+    def forward_backward(self, input_ids: torch.Tensor, labels: torch.Tensor, loss_scale: float = 1.0,
+                         attention_mask: torch.Tensor | None = None) -> torch.Tensor:
+        """Native fast path: one micro-batch forward+backward, grads += loss_scale * dL/dw. Returns the device loss."""
+        return self.engine.forward_backward(input_ids, labels, loss_scale, attention_mask)
+
+    # ------------------------------------------------------------------ state dict / checkpoints
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        res = super().load_state_dict(state_dict, strict=strict, assign=False)
+        self.arena.sync_shadow()
+        return res
+
+    def sync_compute_weights(self) -> None:
+        """Call after writing to parameters outside the fused optimizers (torch optimizers, manual edits)."""
+        self.arena.sync_shadow()
+
+    @classmethod
+    def from_config(cls, config: LlamaConfig, **kw) -> "LlamaForCausalLM":
+        return cls(config, **kw)
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path: str, config: LlamaConfig | None = None, device=None,
+                        precision: str = "bf16-mixed", seed: int | None = 0, **_unused) -> "LlamaForCausalLM":
+        """Load config (+ ``model.safetensors`` if present).  A bare config / preset name yields seeded random init —
+        the offline equivalent of the reference's ``*-fresh`` hub checkpoints (init_weights.py:10-25)."""
+        from ..utils.safetensors_io import load_safetensors
+
+        cfg = config if isinstance(config, LlamaConfig) else LlamaConfig.from_pretrained(pretrained_model_name_or_path)
+        path = Path(pretrained_model_name_or_path)
+        st = path / "model.safetensors" if path.is_dir() else None
+        model = cls(cfg, device=device, precision=precision, seed=seed, init=not (st and st.is_file()))
+        if st is not None and st.is_file():
+            tensors = load_safetensors(str(st))
+            with torch.no_grad():
+                for name in hf_param_order(cfg):
+                    model.arena.p(name).copy_(tensors[name].to(torch.float32))
+            model.arena.sync_shadow()
+        return model
+
+    def save_pretrained(self, directory: str) -> None:
+        from ..utils.safetensors_io import save_safetensors
+
+        os.makedirs(directory, exist_ok=True)
+        self.config.save_pretrained(directory)
+        save_safetensors({n: self.arena.p(n).detach().cpu().contiguous() for n in hf_param_order(self.config)},
+                         os.path.join(directory, "model.safetensors"), metadata={"format": "pt"})
+
+    def num_parameters(self) -> int:
+        return self.config.num_parameters()

@@ -1,0 +1,94 @@
+"""Causal self-attention over the packed qkv buffer.
+
+Layout contract (chosen so that no transpose is ever materialised): the fused QKV GEMM writes
+``qkv[T, (Hq + 2*Hkv) * D]`` with token-major rows; q/k/v are strided *views* ``[B, S, H, D]`` of it and the
+attention output is written token-major ``[T, Hq*D]`` so it feeds the o-proj GEMM directly.
+
+Back-ends:
+  * ``tc``     - our tcgen05 kernel (``csrc/attn_sm100.cu``), used when built and the shape qualifies
+  * ``flash``  - flash-attn 2.8 library kernels (BSHD layout, GQA native)
+  * ``math``   - fp32 PyTorch reference (CPU, tests)
+The reference framework itself calls a library here (torch SDPA / flash-attn: train_fsdp.py:107,173).
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import torch
+
+_FLASH = None
+
+
+def _flash():
+    global _FLASH
+    if _FLASH is None:
+        import flash_attn.flash_attn_interface as fi
+
+        _FLASH = fi
+    return _FLASH
+
+
+def split_qkv(qkv: torch.Tensor, B: int, S: int, Hq: int, Hkv: int, D: int):
+    """Strided [B,S,H,D] views of the packed buffer (no copies)."""
+    row = qkv.shape[1]
+    base = qkv.view(B, S, row)
+    q = base[:, :, : Hq * D].unflatten(-1, (Hq, D))
+    k = base[:, :, Hq * D:(Hq + Hkv) * D].unflatten(-1, (Hkv, D))
+    v = base[:, :, (Hq + Hkv) * D:].unflatten(-1, (Hkv, D))
+    return q, k, v
+
+
+def attention_fwd(qkv: torch.Tensor, B: int, S: int, Hq: int, Hkv: int, D: int):
+    """Returns (out [T, Hq*D], lse).  Causal, scale 1/sqrt(D)."""
+    q, k, v = split_qkv(qkv, B, S, Hq, Hkv, D)
+    scale = 1.0 / math.sqrt(D)
+    if qkv.is_cuda and qkv.dtype in (torch.bfloat16, torch.float16):
+        out, lse, _, rng = _flash()._flash_attn_forward(q, k, v, 0.0, scale, True, -1, -1, 0.0, None, False)
+        return out.view(B * S, Hq * D), (lse, rng)
+    # fp32 math reference
+    qf, kf, vf = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))
+    if Hkv != Hq:
+        rep = Hq // Hkv
+        kf, vf = kf.repeat_interleave(rep, dim=1), vf.repeat_interleave(rep, dim=1)
+    att = (qf @ kf.transpose(-1, -2)) * scale
+    mask = torch.ones(S, S, dtype=torch.bool, device=qkv.device).tril()
+    att = att.masked_fill(~mask, float("-inf"))
+    lse = torch.logsumexp(att, dim=-1)
+    p = torch.softmax(att, dim=-1)
+    out = (p @ vf).permute(0, 2, 1, 3).reshape(B * S, Hq * D).to(qkv.dtype)
+    return out, (lse, None)
+
+
+def attention_bwd(dout: torch.Tensor, qkv: torch.Tensor, out: torch.Tensor, aux, dqkv: torch.Tensor, B: int, S: int,
+                  Hq: int, Hkv: int, D: int) -> torch.Tensor:
+    """Writes dq|dk|dv into the packed ``dqkv`` buffer (same layout as qkv)."""
+    q, k, v = split_qkv(qkv, B, S, Hq, Hkv, D)
+    dq, dk, dv = split_qkv(dqkv, B, S, Hq, Hkv, D)
+    scale = 1.0 / math.sqrt(D)
+    lse, rng = aux
+    if qkv.is_cuda and qkv.dtype in (torch.bfloat16, torch.float16):
+        _flash()._flash_attn_backward(dout.view(B, S, Hq, D), q, k, v, out.view(B, S, Hq, D), lse, dq, dk, dv, 0.0, scale,
+                                      True, -1, -1, 0.0, None, False, rng)
+        return dqkv
+    qf, kf, vf = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))
+    rep = Hq // Hkv
+    if rep != 1:
+        kf, vf = kf.repeat_interleave(rep, dim=1), vf.repeat_interleave(rep, dim=1)
+    att = (qf @ kf.transpose(-1, -2)) * scale
+    mask = torch.ones(S, S, dtype=torch.bool, device=qkv.device).tril()
+    att = att.masked_fill(~mask, float("-inf"))
+    p = torch.softmax(att, dim=-1)
+    do = dout.float().view(B, S, Hq, D).permute(0, 2, 1, 3)
+    dvf = p.transpose(-1, -2) @ do
+    dp = do @ vf.transpose(-1, -2)
+    ds = p * (dp - (dp * p).sum(-1, keepdim=True))
+    dqf = (ds @ kf) * scale
+    dkf = (ds.transpose(-1, -2) @ qf) * scale
+    if rep != 1:
+        dkf = dkf.view(B, Hkv, rep, S, D).sum(2)
+        dvf = dvf.view(B, Hkv, rep, S, D).sum(2)
+    dq.copy_(dqf.permute(0, 2, 1, 3).to(dqkv.dtype))
+    dk.copy_(dkf.permute(0, 2, 1, 3).to(dqkv.dtype))
+    dv.copy_(dvf.permute(0, 2, 1, 3).to(dqkv.dtype))
+    return dqkv

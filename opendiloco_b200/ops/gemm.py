@@ -1,0 +1,53 @@
+"""GEMM entry points used by the training engine.
+
+Three shapes of GEMM appear in a Llama step:
+
+  * ``mm_nt``      y[M,N]  = a[M,K] @ b[N,K]^T          forward linear        (both operands K-major)
+  * ``mm_nn``      y[M,K]  = a[M,N] @ b[N,K]            dgrad                 (b is N-major)
+  * ``mm_tn_acc``  w[N,K] += a[T,N]^T @ b[T,K]  (fp32)  wgrad, accumulated straight into the fp32 gradient arena
+
+Plain (un-fused) GEMMs go to cuBLASLt through ``torch.mm(out=...)``; the fused hot ops (QKV+RoPE, gate|up+SwiGLU,
+LM-head+CE) use the tcgen05 kernels in ``csrc/gemm_sm100.cu`` via :mod:`opendiloco_b200.ops.tc_gemm` when the
+operand shapes qualify.
+"""
+from __future__ import annotations
+
+import torch
+
+_ADDMM_DTYPE_OK: bool | None = None
+
+
+def mm_nt(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    if out is None:
+        return torch.mm(a, b.t())
+    return torch.mm(a, b.t(), out=out)
+
+
+def mm_nn(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    if out is None:
+        return torch.mm(a, b)
+    return torch.mm(a, b, out=out)
+
+
+def mm_tn_acc(a: torch.Tensor, b: torch.Tensor, acc: torch.Tensor, alpha: float = 1.0) -> None:
+    """acc (fp32 [N,K]) += alpha * a^T @ b with low-precision a [T,N], b [T,K] and fp32 accumulation/output."""
+    global _ADDMM_DTYPE_OK
+    if a.dtype == acc.dtype:
+        acc.addmm_(a.t(), b, alpha=alpha)
+        return
+    if a.is_cuda:
+        if _ADDMM_DTYPE_OK is None:
+            try:
+                probe = torch.zeros(8, 8, device=a.device, dtype=torch.float32)
+                x = torch.ones(8, 8, device=a.device, dtype=a.dtype)
+                torch.addmm(probe, x.t(), x, out_dtype=torch.float32, out=probe)
+                _ADDMM_DTYPE_OK = bool(abs(float(probe[0, 0]) - 8.0) < 1e-3)
+            except Exception:
+                _ADDMM_DTYPE_OK = False
+        if _ADDMM_DTYPE_OK:
+            torch.addmm(acc, a.t(), b, out_dtype=torch.float32, alpha=alpha, out=acc)
+            return
+        tmp = torch.mm(a.t(), b, out_dtype=torch.float32)
+        acc.add_(tmp, alpha=alpha)
+        return
+    acc.add_(a.float().t() @ b.float(), alpha=alpha)
