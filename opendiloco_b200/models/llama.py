@@ -356,6 +356,7 @@ class LlamaForCausalLM(nn.Module):
             prm = nn.Parameter(ar.p(name), requires_grad=True)
             prm.grad = ar.g(name)
             prm._odb_name = name
+            prm._odb_arena = ar
             return prm
 
         self.model = _Holder()
@@ -481,3 +482,17 @@ class LlamaForCausalLM(nn.Module):
 
     def num_parameters(self) -> int:
         return self.config.num_parameters()
+
+    @torch.no_grad()
+    def clip_grad_norm_(self, max_norm: float, norm_type: float = 2.0) -> torch.Tensor:
+        """FSDP-style method the reference calls (train_fsdp.py:395).  If a FusedAdamW owns the arena the scaling is
+        folded into its next step (one reduction pass, zero extra sweeps); otherwise grads are scaled here."""
+        assert norm_type == 2.0
+        ref = getattr(self.arena, "fused_optimizer", None)
+        opt = ref() if ref is not None else None
+        if opt is not None:
+            return opt.compute_grad_norm_partials(max_norm)
+        total = self.arena.grad.norm(2)
+        coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+        self.arena.grad.mul_(coef)
+        return total

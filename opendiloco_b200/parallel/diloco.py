@@ -1,0 +1,758 @@
+"""DiLoCo: inner optimizer every step, outer (pseudo-gradient) step every ``num_inner_steps``.
+
+Public surface mirrors the reference's ``open_diloco.hivemind_diloco``:
+``DiLoCoOptimizer``, ``DiLoCoGradAverager``, ``DiLoCoStateAverager``, ``DiloCoProgressTracker``, ``AllReduceStrategy``.
+The machinery underneath is different by design:
+
+  * theta_outer, the pseudo-gradient and the outer momentum are flat fp32 buffers RESIDENT IN HBM (the reference
+    keeps them on the CPU in shared memory: hivemind_diloco.py:400, train_diloco_torch.py:132-135);
+  * the pseudo-gradient all-reduce is ONE collective on the flat buffer over NCCL/NVLink, or - when an NVLink
+    symmetric-memory window is available - a single fused kernel that computes theta_outer - theta_local, reduces it
+    through the switch (multimem) and applies Nesterov in the same launch (``parallel/fused_outer.py``);
+  * the outer SGD-Nesterov update, the theta_local reset and the bf16 shadow refresh are one kernel
+    (``csrc/optim.cu``) instead of foreach SGD + 111 copies (train_diloco_torch.py:346-353).
+
+Algorithm (reference: hivemind_diloco.py:483-558,570-679 ; train_diloco_torch.py:336-353):
+    every step:      inner.step() ; samples += batch_size
+    every H steps:   delta = theta_outer - theta_local ; delta <- mean over workers ;
+                     theta_outer <- SGD_nesterov(theta_outer, delta) ; theta_local <- theta_outer ; epoch += 1
+Inner AdamW moments and the LR schedule are NOT reset at outer steps.
+"""
+from __future__ import annotations
+
+import contextlib
+import time
+from enum import Enum
+from typing import Callable, Iterable
+
+import torch
+import torch.distributed as dist
+
+from ..ops import kernels as K
+from ..optim.fused import FlatView, flatten_params
+from ..utils.logger import get_logger
+from . import comm
+from .swarm import (DHT, GlobalTrainingProgress, LocalTrainingProgress, PerformanceEMA, StepControl, get_dht_time)
+
+logger = get_logger()
+
+
+class AllReduceStrategy(Enum):
+    """When to trigger the pseudo-gradient averaging round (reference: hivemind_diloco.py:285-297).
+
+    WAIT_FOR_ALL: wait (up to ``timeout_waiting_for_peers``) until every worker finished its local steps.
+    NO_WAIT:      the fastest worker triggers the round after ``matchmaking_time``; workers that have not arrived by
+                  then are left out of this round and re-synchronise from their peers afterwards.
+    """
+
+    WAIT_FOR_ALL = "WAIT_FOR_ALL"
+    NO_WAIT = "NO_WAIT"
+
+
+DEFAULT_TIMEOUT_WAITING_FOR_PEERS = 600
+
+
+# ====================================================================================================== progress tracker
+class DiloCoProgressTracker:
+    """Local/global progress bookkeeping (reference: hivemind_diloco.py:174-282 on top of hivemind.ProgressTracker).
+
+    An epoch (= one outer step) is ready when THIS worker accumulated ``target_batch_size = batch_size * H`` samples
+    or when the swarm is already ahead.  Peers publish (epoch, samples, samples/s) through the c10d store so that
+    ``global_progress`` / ETA mean the same thing as in the reference.
+    """
+
+    def __init__(self, batch_size: int, num_inner_steps: int, *, dht: DHT | None = None, prefix: str = "diloco",
+                 target_batch_size: int | None = None, min_refresh_period: float = 0.5, max_refresh_period: float = 2.0,
+                 default_refresh_period: float = 1.0, performance_ema_alpha: float = 0.1, publish: bool = False,
+                 **_ignored):
+        self.batch_size, self.num_inner_steps = batch_size, num_inner_steps
+        self.dht, self.prefix = dht, prefix
+        self.target_batch_size = target_batch_size if target_batch_size is not None else batch_size * num_inner_steps
+        self.min_refresh_period, self.max_refresh_period = min_refresh_period, max_refresh_period
+        self.default_refresh_period = default_refresh_period
+        self.performance_ema = PerformanceEMA(alpha=performance_ema_alpha)
+        self.local_progress = LocalTrainingProgress(peer_id=dht.peer_id if dht else "worker-0")
+        self._global_epoch_hint = 0
+        self._paused = False
+        self._publish = publish
+        self.global_progress = self._make_global()
+
+    # -- reference properties ------------------------------------------------------------------
+    @property
+    def num_peers(self) -> int:
+        return self.dht.num_peers if self.dht is not None else 1
+
+    @property
+    def global_epoch(self) -> int:
+        return max(self._global_epoch_hint, self.local_progress.epoch)
+
+    @property
+    def ready_to_update_epoch(self) -> bool:
+        return (self.global_epoch > self.local_progress.epoch
+                or self.local_progress.samples_accumulated >= self.target_batch_size)
+
+    @property
+    def estimated_next_update_time(self) -> float:
+        """Seconds until this peer reaches its local steps (0 when ready).  The reference returns an absolute time in
+        the ready case and a duration otherwise; callers compare it with a duration, so a
+        duration is returned in both cases."""
+        if self.ready_to_update_epoch:
+            return 0.0
+        remaining = max(0, self.target_batch_size - self.local_progress.samples_accumulated)
+        return remaining / max(self.performance_ema.samples_per_second, 1e-9)
+
+    @property
+    def local_step(self) -> int:
+        return self.local_progress.samples_accumulated // self.batch_size
+
+    @property
+    def real_step(self) -> int:
+        return self.local_step + self.local_progress.epoch * self.num_inner_steps
+
+    # -- updates -----------------------------------------------------------------------------
+    def _make_global(self) -> GlobalTrainingProgress:
+        now = get_dht_time()
+        eta = self.estimated_next_update_time
+        return GlobalTrainingProgress(epoch=self.global_epoch, samples_accumulated=self.local_progress.samples_accumulated,
+                                      target_batch_size=self.target_batch_size, num_peers=self.num_peers, num_clients=0,
+                                      eta_next_epoch=now + eta,
+                                      next_fetch_time=now + min(max(eta, self.min_refresh_period), self.max_refresh_period))
+
+    def report_local_progress(self, local_epoch: int, samples_accumulated: int, update_global_samples: bool = True) -> None:
+        extra = samples_accumulated - self.local_progress.samples_accumulated
+        if extra > 0 and not self._paused:
+            self.performance_ema.update(task_size=extra)
+        self.local_progress.epoch = local_epoch
+        self.local_progress.samples_accumulated = samples_accumulated
+        self.local_progress.samples_per_second = self.performance_ema.samples_per_second
+        self.local_progress.time = get_dht_time()
+        self.global_progress = self._make_global()
+        if self._publish:
+            self._publish_progress()
+
+    def update_epoch(self, new_epoch: int | None = None) -> int:
+        if new_epoch is None:
+            new_epoch = self.local_progress.epoch + 1
+        self._global_epoch_hint = max(self._global_epoch_hint, new_epoch)
+        self.local_progress.epoch = new_epoch
+        self.local_progress.samples_accumulated = 0
+        self.performance_ema.reset_timer()
+        self.global_progress = self._make_global()
+        return new_epoch
+
+    @contextlib.contextmanager
+    def pause_updates(self):
+        """Freeze throughput accounting (used around the outer step and checkpoint writes: hivemind_diloco.py:610,
+        train_fsdp.py:478)."""
+        self._paused = True
+        try:
+            with self.performance_ema.pause():
+                yield
+        finally:
+            self._paused = False
+
+    # -- optional cross-worker visibility through the rendezvous store ------------------------------
+    def _publish_progress(self) -> None:
+        store = self.dht.store() if self.dht is not None else None
+        if store is None:
+            return
+        lp = self.local_progress
+        store.set(f"{self.prefix}_progress/{lp.peer_id}",
+                  f"{lp.epoch},{lp.samples_accumulated},{lp.samples_per_second:.6f},{lp.time:.3f}")
+
+    def fetch_global_progress(self) -> GlobalTrainingProgress:
+        """Read every peer's published record; ETA = max over peers of their remaining time (hivemind_diloco.py:248-256)."""
+        store = self.dht.store() if self.dht is not None else None
+        if store is None or not self._publish:
+            return self.global_progress
+        now = get_dht_time()
+        eta, epoch, alive = 0.0, self.local_progress.epoch, 0
+        for pid in self.dht.peer_ids():
+            try:
+                if not store.check([f"{self.prefix}_progress/{pid}"]):
+                    continue
+                e, s, sps, _t = store.get(f"{self.prefix}_progress/{pid}").decode().split(",")
+            except Exception:
+                continue
+            alive += 1
+            epoch = max(epoch, int(e))
+            if int(e) >= epoch:
+                eta = max(eta, max(0, self.target_batch_size - int(s)) / max(float(sps), 1e-9))
+        self._global_epoch_hint = max(self._global_epoch_hint, epoch)
+        self.global_progress = GlobalTrainingProgress(epoch, 0, self.target_batch_size, num_peers=max(alive, 1),
+                                                      num_clients=0, eta_next_epoch=now + eta,
+                                                      next_fetch_time=now + min(max(eta, self.min_refresh_period),
+                                                                                self.max_refresh_period))
+        return self.global_progress
+
+
+# ====================================================================================================== gradient averager
+class DiLoCoGradAverager:
+    """Averages pseudo-gradients across workers; the averaged tensors ARE the ``.grad`` buffers of the outer
+    ("offloaded") optimizer (reference: hivemind_diloco.py:61-171).
+
+    ``flat=(theta_outer, delta, theta_local)`` is supplied by DiLoCoOptimizer when everything lives in flat buffers;
+    stand-alone use with arbitrary parameters (reference test tests/test_diloco_hivemind.py:53-96) stages through a
+    temporary flat buffer.
+    """
+
+    def __init__(self, main_parameters, offloaded_optimizer: torch.optim.Optimizer, *, dht: DHT | None = None,
+                 prefix: str = "diloco_grad_averager", warn: bool = True, compression=None, flat=None,
+                 min_matchmaking_time: float = 5.0, **kwargs):
+        if kwargs.pop("client_mode", None):
+            raise KeyError("client_mode is not supported in DiLoCoGradAverager")
+        if "averaged_grads" in kwargs:
+            raise KeyError("DiLoCoGradAverager does not support averaged_grads: it uses the offloaded optimizer gradients")
+        if not isinstance(main_parameters, (list, tuple)):
+            raise ValueError("main_parameters must be a list or tuple of parameters, not an iterator")
+        self.main_parameters = list(main_parameters)
+        self.offloaded_optimizer = offloaded_optimizer
+        self.dht, self.prefix, self.warn = dht, prefix, warn
+        self.compression = compression
+        self.matchmaking_kwargs = {"min_matchmaking_time": min_matchmaking_time}
+        self.local_samples_accumulated = 0
+        self.local_times_accumulated = 0
+        self._new_averaged_grads = False
+        self._flat = flat
+        self._averaged_grads = tuple(self._grads_from_optimizer())
+        self.last_allreduce_seconds = 0.0
+
+    @property
+    def peer_id(self) -> str:
+        return self.dht.peer_id if self.dht is not None else "worker-0"
+
+    @property
+    def group(self):
+        return self.dht.group if self.dht is not None else None
+
+    def _offloaded_params(self) -> list[torch.Tensor]:
+        return [p for g in self.offloaded_optimizer.param_groups for p in g["params"]]
+
+    def _grads_from_optimizer(self):
+        for p in self._offloaded_params():
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            yield p.grad
+
+    @contextlib.contextmanager
+    def get_tensors(self):
+        yield self._averaged_grads
+
+    # -- scheduling (matchmaking is a no-op on a static NVLink group; the handle keeps the reference's call pattern)
+    def schedule_step(self, scheduled_time: float | None = None, **kwargs) -> StepControl:
+        assert kwargs.get("weight") is None, "setting weight in schedule_step is not supported"
+        return StepControl(scheduled_time=scheduled_time)
+
+    @torch.no_grad()
+    def compute_and_load_pseudo_grad_into_averager(self) -> None:
+        """delta = theta_outer - theta_local into the outer optimizer's grad buffers (hivemind_diloco.py:158-167)."""
+        if self._flat is not None:
+            theta_outer, delta, theta_local = self._flat
+            if delta.device == theta_local.device:
+                K.pseudo_grad(theta_outer, theta_local, delta)
+            else:
+                delta.copy_(theta_outer - theta_local.to(theta_outer.device))
+            return
+        for opt_p, g, main_p in zip(self._offloaded_params(), self._averaged_grads, self.main_parameters):
+            g.copy_(opt_p.data - main_p.detach().to(opt_p.device), non_blocking=True)
+
+    @torch.no_grad()
+    def _all_reduce(self) -> None:
+        group = self.group
+        if comm.group_size(group) <= 1:
+            return
+        t0 = time.perf_counter()
+        if self._flat is not None:
+            buf = self._flat[1]
+            if self.compression is not None and not self.compression.is_identity:
+                self.compression.all_reduce_mean_(buf, group)
+            else:
+                comm.all_reduce_avg_(_collective_view(buf), group)
+                if not buf.is_cuda and dist.get_backend(group) == "nccl":   # CPU-offloaded theta_outer, NCCL group
+                    raise RuntimeError("offload_device='cpu' needs a gloo group")
+        else:
+            grads = list(self._averaged_grads)
+            dev = comm_device(group, grads[0].device)
+            flat = torch.cat([g.reshape(-1).to(dev, torch.float32) for g in grads])
+            if self.compression is not None and not self.compression.is_identity:
+                self.compression.all_reduce_mean_(flat, group)
+            else:
+                comm.all_reduce_avg_(flat, group)
+            off = 0
+            for g in grads:
+                g.copy_(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
+        self.last_allreduce_seconds = time.perf_counter() - t0
+
+    def step(self, control: StepControl | None = None, timeout: float | None = None, wait: bool = True, **kwargs):
+        """Compute the pseudo-gradient, average it with the peers, leave the mean in the outer grads
+        (hivemind_diloco.py:134-156).  Returns {peer_id: None} for every member of the round (or the control if
+        ``wait=False``; the collective itself is stream-ordered, nothing runs on a background thread)."""
+        if control is None:
+            control = self.schedule_step(timeout=timeout, **kwargs)
+        self.compute_and_load_pseudo_grad_into_averager()
+        control.allow_allreduce()
+        try:
+            self._all_reduce()
+            self._new_averaged_grads = True
+            members = self.dht.peer_ids() if self.dht is not None else [self.peer_id]
+            control.set_result({pid: None for pid in members})
+        except BaseException as e:  # surfaced through control.result(), like an MPFuture
+            control.set_exception(e)
+        return control.result(timeout) if wait else control
+
+    def notify_used_averaged_gradients(self) -> None:
+        self._new_averaged_grads = False
+
+    def shutdown(self) -> None:
+        pass
+
+
+def _collective_view(buf: torch.Tensor) -> torch.Tensor:
+    return buf
+
+
+def comm_device(group, fallback: torch.device) -> torch.device:
+    if group is not None and dist.is_initialized() and dist.get_backend(group) == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return fallback
+
+
+# ====================================================================================================== state averager
+class DiLoCoStateAverager:
+    """Owns theta_outer ("offloaded" parameters), the outer optimizer built on it, the inner optimizer and its LR
+    scheduler (reference: hivemind_diloco.py:35-58 on top of hivemind.TrainingStateAverager).
+    The scheduler is attached to the INNER optimizer only; the outer optimizer never sees it."""
+
+    def __init__(self, *, params, optimizer: Callable, inner_optimizer: torch.optim.Optimizer, num_inner_steps: int,
+                 scheduler: Callable | None = None, dht: DHT | None = None, prefix: str = "diloco_state_averager",
+                 offload_device: str | torch.device | None = None, flat_view: FlatView | None = None,
+                 average_state_every: int = 0, **_ignored):
+        self.dht, self.prefix = dht, prefix
+        self.inner_optimizer, self.num_inner_steps = inner_optimizer, num_inner_steps
+        self.main_parameters = list(params)
+        self.fv = flat_view if flat_view is not None else flatten_params(self.main_parameters)
+        dev = self.fv.flat.device if offload_device is None else torch.device(offload_device)
+        self.theta_local = self.fv.own(self.fv.flat)          # the slice of the master weights this rank owns
+        self.shadow_local = self.fv.own(self.fv.shadow)
+        self.theta_outer = self.theta_local.detach().to(dev, copy=True)
+        self.delta = torch.zeros_like(self.theta_outer)
+        self.momentum_buffer: torch.Tensor | None = None
+        self.offloaded_parameters = []
+        if self.fv.sharded:
+            # ZeRO-sharded worker: parameter boundaries do not align with the shard, the outer optimizer sees one
+            # flat parameter (SGD is element-wise, so the update is identical)
+            op = torch.nn.Parameter(self.theta_outer, requires_grad=True)
+            op.grad = self.delta
+            self.offloaded_parameters.append(op)
+        else:
+            for i, _ in enumerate(self.fv.params):
+                op = torch.nn.Parameter(self.fv.view_of(self.theta_outer, i), requires_grad=True)
+                op.grad = self.fv.view_of(self.delta, i)
+                self.offloaded_parameters.append(op)
+        self.optimizer: torch.optim.Optimizer = optimizer(self.offloaded_parameters)
+        self.scheduler_inner_optimizer = scheduler(self.inner_optimizer) if scheduler is not None else None
+        self.local_epoch = 0
+        self.averaging_in_progress = False
+        self.state_sharing_priority = 0
+        self.custom_gradients = True
+        self.offload_optimizer = True
+        self.average_state_every = average_state_every
+        self._adopt_sgd_momentum()
+
+    # -- fused-kernel eligibility: torch.optim.SGD with plain (Nesterov) momentum -----------------------
+    def _sgd_hparams(self):
+        opt = self.optimizer
+        if type(opt) is not torch.optim.SGD or len(opt.param_groups) != 1:
+            return None
+        g = opt.param_groups[0]
+        if g.get("dampening", 0) != 0 or g.get("weight_decay", 0) != 0 or g.get("maximize", False):
+            return None
+        return g
+
+    def _adopt_sgd_momentum(self) -> None:
+        """Give torch.optim.SGD momentum buffers that are views of ONE flat buffer, so the fused kernel and the torch
+        state_dict see the same memory.  A zero buffer is equivalent to torch's lazily created one
+        (first step: buf = 0*mu + g)."""
+        g = self._sgd_hparams()
+        if g is None or g.get("momentum", 0) == 0:
+            return
+        if self.momentum_buffer is None:
+            self.momentum_buffer = torch.zeros_like(self.theta_outer)
+        for i, op in enumerate(self.offloaded_parameters):
+            st = self.optimizer.state[op]
+            view = self.momentum_buffer if self.fv.sharded else self.fv.view_of(self.momentum_buffer, i)
+            if "momentum_buffer" in st and st["momentum_buffer"] is not None and st["momentum_buffer"].data_ptr() != view.data_ptr():
+                view.copy_(st["momentum_buffer"])
+            st["momentum_buffer"] = view
+
+    def reload_optimizer_state(self) -> None:
+        """Call after ``self.optimizer.load_state_dict`` (torch replaces state tensors with copies)."""
+        self._adopt_sgd_momentum()
+
+    # -- the outer step ---------------------------------------------------------------------------------
+    @torch.no_grad()
+    def step(self, *, increment_epoch: bool = True, optimizer_step: bool = True, averaging_round: bool = False,
+             zero_grad: bool = False, fused_solo: bool = False, **_ignored) -> None:
+        """Outer optimizer step on theta_outer using the (already averaged) pseudo-gradient in its .grad buffers, then
+        theta_local <- theta_outer.  ``fused_solo``: single-worker form, delta computed inside the kernel."""
+        if optimizer_step:
+            g = self._sgd_hparams()
+            same_dev = self.theta_outer.device == self.theta_local.device
+            if g is not None and same_dev and (g.get("momentum", 0) != 0):
+                K.nesterov_outer(self.theta_outer, self.momentum_buffer, None if fused_solo else self.delta,
+                                 self.theta_local, self.shadow_local, g["lr"], g["momentum"], bool(g.get("nesterov", False)))
+                self.fv.gather_compute_weights()
+            else:
+                if fused_solo:
+                    K.pseudo_grad(self.theta_outer, self.theta_local.to(self.theta_outer.device), self.delta)
+                self.optimizer.step()
+                self.apply_optimizer_parameters()
+        if averaging_round and comm.group_size(self.dht.group if self.dht else None) > 1:
+            self.average_state()
+        if zero_grad:
+            self.delta.zero_()
+        if increment_epoch:
+            self.local_epoch += 1
+
+    @torch.no_grad()
+    def apply_optimizer_parameters(self) -> None:
+        """theta_local <- theta_outer (+ compute-dtype shadow).  hivemind: _apply_optimizer_parameters_."""
+        self.theta_local.copy_(self.theta_outer, non_blocking=True)
+        if self.shadow_local is not None:
+            if self.shadow_local.dtype == torch.bfloat16:
+                K.cast_to_bf16(self.theta_local, self.shadow_local)
+            else:
+                self.shadow_local.copy_(self.theta_local)
+        self.fv.gather_compute_weights()
+
+    @torch.no_grad()
+    def average_state(self) -> None:
+        """Parameter (+momentum) averaging round - the drift-repair path (reference H2, hivemind_diloco.py:654-665)."""
+        group = self.dht.group if self.dht else None
+        comm.all_reduce_avg_(self.theta_outer, group)
+        if self.momentum_buffer is not None:
+            comm.all_reduce_avg_(self.momentum_buffer, group)
+        self.apply_optimizer_parameters()
+
+    @torch.no_grad()
+    def load_state_from_peers(self, src: int = 0) -> None:
+        """Download theta_outer, outer-optimizer state and the epoch from a peer (reference H3)."""
+        group = self.dht.group if self.dht else None
+        if comm.group_size(group) <= 1:
+            return
+        comm.broadcast_(self.theta_outer, src, group)
+        if self.momentum_buffer is not None:
+            comm.broadcast_(self.momentum_buffer, src, group)
+        ep = torch.tensor([self.local_epoch], dtype=torch.int64, device=comm_device(group, torch.device("cpu")))
+        comm.broadcast_(ep, src, group)
+        self.local_epoch = int(ep.item())
+        self.apply_optimizer_parameters()
+
+
+# ====================================================================================================== the optimizer
+class DiLoCoOptimizer:
+    """Two-level DiLoCo optimizer with the constructor/attribute surface of the reference class
+    (hivemind_diloco.py:303-738).
+
+    :param dht: swarm handle (``opendiloco_b200.parallel.swarm.DHT``); None = this process is the only worker.
+    :param batch_size: samples contributed per ``step()`` call
+    :param num_inner_steps: H, inner steps per outer step
+    :param outer_optimizer: factory ``params -> torch.optim.Optimizer`` (DiLoCo: SGD lr 0.7, momentum 0.9, nesterov)
+    :param inner_optimizer: optimizer instance or factory ``params -> optimizer`` (DiLoCo: AdamW)
+    :param scheduler: factory ``inner_optimizer -> LRScheduler`` (stepped once per inner step)
+    :param grad_compression: codec from ``opendiloco_b200.parallel.compression`` applied to the pseudo-gradient round
+    :param offload_device: where theta_outer lives; default = the parameters' device (HBM)
+    """
+
+    def __init__(self, *, dht: DHT | None = None, run_id: str = "diloco", batch_size: int, num_inner_steps: int,
+                 outer_optimizer: Callable, inner_optimizer, params: Iterable | None = None,
+                 scheduler: Callable | None = None, averager_opts: dict | None = None, grad_compression=None,
+                 tracker_opts: dict | None = None, all_reduce_strategy: AllReduceStrategy = AllReduceStrategy.WAIT_FOR_ALL,
+                 timeout_waiting_for_peers: float | None = None, matchmaking_time: float | None = 15.0,
+                 averaging_timeout: float | None = 60.0, average_state_every: int = 0, verbose: bool = False,
+                 offload_device=None, fused_collective: bool | None = None, **kwargs):
+        self._check_kwargs(kwargs)
+        all_reduce_strategy = AllReduceStrategy(all_reduce_strategy) if not isinstance(all_reduce_strategy, AllReduceStrategy) \
+            else all_reduce_strategy
+        if timeout_waiting_for_peers is not None and all_reduce_strategy == AllReduceStrategy.NO_WAIT:
+            raise ValueError("You cannot use timeout_waiting_for_peers with NO_WAIT strategy, use WAIT_FOR_ALL instead")
+        if timeout_waiting_for_peers is not None and matchmaking_time is not None and timeout_waiting_for_peers < matchmaking_time:
+            raise ValueError("timeout_waiting_for_peers must be greater than matchmaking_time")
+        if all_reduce_strategy == AllReduceStrategy.WAIT_FOR_ALL and timeout_waiting_for_peers is None:
+            timeout_waiting_for_peers = DEFAULT_TIMEOUT_WAITING_FOR_PEERS
+        for factory in (outer_optimizer, scheduler):
+            if not (callable(factory) or factory is None):
+                raise TypeError("You need to pass inner and outer optimizer as well as scheduler as callable")
+        if params is None:
+            raise ValueError("params is required")
+        params = list(params)   # model.parameters() is a generator and two optimizers consume it
+
+        self.dht, self.run_id = dht, run_id
+        self.all_reduce_strategy, self.timeout_waiting_for_peers = all_reduce_strategy, timeout_waiting_for_peers
+        self.matchmaking_time = matchmaking_time if matchmaking_time is not None else 15.0
+        self.averaging_timeout = averaging_timeout
+        self.num_inner_steps, self.batch_size_per_step = num_inner_steps, batch_size
+        self.average_state_every = average_state_every
+        self.status_loglevel = 20 if verbose else 10
+        self.client_mode = self.auxiliary = False
+        self.delay_optimizer_step = self.delay_grad_averaging = self.delay_state_averaging = False
+        self.scheduled_diloco_grads: StepControl | None = None
+        self.scheduled_state: StepControl | None = None
+
+        if isinstance(inner_optimizer, torch.optim.Optimizer):
+            self.inner_optimizer = inner_optimizer
+        elif callable(inner_optimizer):
+            self.inner_optimizer = inner_optimizer(params=params) if _accepts_kw(inner_optimizer) else inner_optimizer(params)
+        else:
+            raise TypeError(f"Expected inner_optimizer to be an Optimizer or a factory, got {type(inner_optimizer)}")
+
+        fv = getattr(self.inner_optimizer, "fv", None)     # FusedAdamW already flattened the parameters
+        self.state_averager = DiLoCoStateAverager(params=params, optimizer=outer_optimizer,
+                                                  inner_optimizer=self.inner_optimizer, num_inner_steps=num_inner_steps,
+                                                  scheduler=scheduler, dht=dht, prefix=f"{run_id}_state_averager",
+                                                  offload_device=offload_device, flat_view=fv,
+                                                  average_state_every=average_state_every, **(averager_opts or {}))
+        sa = self.state_averager
+        self.diloco_grad_averager = DiLoCoGradAverager(
+            main_parameters=sa.main_parameters, offloaded_optimizer=sa.optimizer, dht=dht,
+            prefix=f"{run_id}_grad_averager", compression=grad_compression,
+            flat=(sa.theta_outer, sa.delta, sa.theta_local), min_matchmaking_time=self.matchmaking_time)
+        topts = dict(tracker_opts or {})
+        topts.pop("private_key", None)
+        topts.setdefault("max_refresh_period", 2)
+        self.tracker = DiloCoProgressTracker(batch_size, num_inner_steps, dht=dht, prefix=run_id,
+                                             target_batch_size=batch_size * num_inner_steps,
+                                             publish=all_reduce_strategy == AllReduceStrategy.NO_WAIT, **topts)
+        self._schema_hash = self._compute_schema_hash()
+        self._fused = None
+        want_fused = fused_collective if fused_collective is not None else True
+        if want_fused and self.num_peers > 1 and sa.theta_outer.is_cuda and (grad_compression is None or grad_compression.is_identity
+                                                                              or getattr(grad_compression, "fusable", False)):
+            from .fused_outer import try_make_fused_outer
+
+            self._fused = try_make_fused_outer(self, grad_compression)
+        self.last_outer_step_seconds = 0.0
+
+    # ------------------------------------------------------------------------------------------ validation
+    @staticmethod
+    def _check_kwargs(kwargs: dict) -> None:
+        """Same rejections as the reference (hivemind_diloco.py:408-444)."""
+        if "optimizer" in kwargs:
+            raise KeyError("optimizer should not be passed to DiLoCoOptimizer, pass rather to outer_optimizer")
+        if "use_local_updates" in kwargs:
+            if kwargs.pop("use_local_updates") is False:
+                raise ValueError("You cannot use DiLoCo without local updates")
+        if "offload_optimizer" in kwargs:
+            if kwargs.pop("offload_optimizer") is False:
+                raise ValueError("offload_optimizer=False, is not supported in DiLoCo for now")
+        for name in ("delay_state_averaging", "delay_grad_averaging", "delay_optimizer_step"):
+            if kwargs.pop(name, False) is True:
+                raise ValueError(f"{name} is not supported in DiLoCo for now")
+        if "target_batch_size" in kwargs:
+            raise KeyError("DiLoCo does not have a target_batch_size, use batch_size with num_inner_steps")
+        if "batch_size_per_step" in kwargs:
+            raise KeyError("DiLoCo does not have a batch_size_per_step, use batch_size instead")
+        # hivemind transport knobs that have no meaning on NVLink are accepted and ignored
+        for name in ("state_averaging_compression", "load_state_compression", "allreduce_timeout", "next_chunk_timeout",
+                     "load_state_timeout", "shutdown_timeout", "reuse_grad_buffers", "grad_averager_factory",
+                     "state_averager_opts", "extra_tensors", "request_timeout", "target_group_size", "part_size_bytes"):
+            kwargs.pop(name, None)
+        if kwargs:
+            raise TypeError(f"unexpected arguments for DiLoCoOptimizer: {sorted(kwargs)}")
+
+    def _compute_schema_hash(self) -> int:
+        return hash(tuple(tuple(p.shape) for p in self.state_averager.offloaded_parameters))
+
+    # ------------------------------------------------------------------------------------------ views
+    @property
+    def num_peers(self) -> int:
+        return self.dht.num_peers if self.dht is not None else 1
+
+    @property
+    def local_epoch(self) -> int:
+        return self.state_averager.local_epoch
+
+    @property
+    def param_groups(self):
+        """Inner optimizer is the main optimizer (hivemind_diloco.py:692-695)."""
+        return self.inner_optimizer.param_groups
+
+    @property
+    def state(self):
+        return self.inner_optimizer.state
+
+    # ------------------------------------------------------------------------------------------ step
+    def step(self, closure: Callable | None = None, batch_size: int | None = None, scaler=None):
+        """Inner step; every ``num_inner_steps`` calls also the outer step (hivemind_diloco.py:483-558).
+        ``scaler``: a GradScaler applied to the INNER step only - pseudo-gradients are never scaled."""
+        if scaler is not None and closure is not None:
+            raise ValueError("You cannot use closure and scaler at the same time")
+        batch_size = batch_size if batch_size is not None else self.batch_size_per_step
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        if self._should_load_state_from_peers():
+            logger.log(self.status_loglevel, "Peer is out of sync")
+            self.load_state_from_peers()
+            return loss
+        self.tracker.report_local_progress(self.local_epoch, self.tracker.local_progress.samples_accumulated + batch_size)
+        self._maybe_schedule_gradient_averaging()
+        if scaler is not None:
+            scaler.step(self.inner_optimizer)
+            from ..utils.training import found_inf_grad
+
+            if found_inf_grad(self.inner_optimizer, scaler):
+                logger.log(self.status_loglevel, f"Found inf grad at step {self.tracker.real_step}")
+        else:
+            self.inner_optimizer.step()
+        if self.state_averager.scheduler_inner_optimizer is not None:
+            self.state_averager.scheduler_inner_optimizer.step()
+        if self.tracker.ready_to_update_epoch:
+            self._update_global_epoch()
+        return loss
+
+    def _should_load_state_from_peers(self) -> bool:
+        return self.tracker.global_epoch > self.local_epoch + 1 and self.num_peers > 1
+
+    def _maybe_schedule_gradient_averaging(self) -> None:
+        """Pre-schedule the round when the epoch is about to end (hivemind_diloco.py:722-738)."""
+        if self.num_peers <= 1:
+            return
+        if self.all_reduce_strategy == AllReduceStrategy.WAIT_FOR_ALL:
+            eta = self.tracker.global_progress.eta_next_epoch - get_dht_time()
+        else:
+            eta = self.tracker.estimated_next_update_time
+        if eta <= self.matchmaking_time:
+            c = self.scheduled_diloco_grads
+            if c is None or c.triggered or c.done():
+                self.scheduled_diloco_grads = self.diloco_grad_averager.schedule_step(timeout=self.averaging_timeout)
+
+    def _wait_for_peers(self) -> list[int] | None:
+        """Arrival handshake through the rendezvous store.  Returns the ranks (in the outer group) that take part in
+        this round, or None for "everyone".  WAIT_FOR_ALL waits up to ``timeout_waiting_for_peers`` for the slowest
+        worker (hivemind_diloco.py:578-608); NO_WAIT gives late workers ``matchmaking_time`` seconds."""
+        store = self.dht.store() if self.dht is not None else None
+        n = self.num_peers
+        if store is None or n <= 1:
+            return None
+        if self.all_reduce_strategy == AllReduceStrategy.WAIT_FOR_ALL and self.timeout_waiting_for_peers is None:
+            return None
+        epoch, me = self.local_epoch, self.dht.rank_in_group
+        key = lambda r: f"{self.run_id}/arrive/{epoch}/{r}"  # noqa: E731
+        store.set(key(me), "1")
+        budget = self.timeout_waiting_for_peers if self.all_reduce_strategy == AllReduceStrategy.WAIT_FOR_ALL \
+            else self.matchmaking_time
+        deadline = time.perf_counter() + float(budget)
+        keys = [key(r) for r in range(n)]
+        while time.perf_counter() < deadline:
+            try:
+                if store.check(keys):
+                    return None
+            except Exception:
+                return None
+            time.sleep(0.005)
+        present = [r for r in range(n) if store.check([key(r)])]
+        logger.log(self.status_loglevel, f"Timeout waiting for peers, going to skip slowest peers; present={present}")
+        return present
+
+    def _update_global_epoch(self) -> None:
+        """The outer step (hivemind_diloco.py:570-679)."""
+        assert self._schema_hash == self._compute_schema_hash(), "parameters changed during iteration"
+        t_start = time.perf_counter()
+        sa, ga = self.state_averager, self.diloco_grad_averager
+        present = self._wait_for_peers() if self.num_peers > 1 else None
+        if present is not None and len(present) < self.num_peers:
+            raise RuntimeError(
+                f"DiLoCo worker(s) missing at outer step {self.local_epoch}: present ranks {present} of {self.num_peers}. "
+                "Static NVLink groups cannot shrink mid-collective; restart from the last checkpoint "
+                "(--hv.fail_rank_drop semantics, train_fsdp.py:452-457).")
+        with self.tracker.pause_updates():
+            next_epoch = max(self.local_epoch + 1, self.tracker.global_epoch)
+            average_state = (self.num_peers > 1 and self.average_state_every > 0
+                             and next_epoch % self.average_state_every == 0)
+            if self._fused is not None:
+                self._fused.outer_step()                    # pseudo-grad + NVLink reduce + Nesterov in ONE kernel
+                sa.step(increment_epoch=True, optimizer_step=False, averaging_round=average_state)
+            elif self.num_peers > 1:
+                logger.log(self.status_loglevel, f"Beginning optimizer step #{self.local_epoch}")
+                ga.step(wait=True, timeout=self.averaging_timeout, control=self.scheduled_diloco_grads)
+                logger.log(self.status_loglevel, f"Time taken for gradient all reduce: {ga.last_allreduce_seconds} sec")
+                ga.notify_used_averaged_gradients()
+                self.scheduled_diloco_grads = None
+                sa.step(increment_epoch=True, optimizer_step=True, averaging_round=average_state)
+            else:
+                sa.step(increment_epoch=True, optimizer_step=True, averaging_round=False, fused_solo=True)
+            if self.scheduled_state is not None and not self.scheduled_state.done():
+                self.scheduled_state.cancel()
+            self.scheduled_state = None
+            self.tracker.update_epoch(new_epoch=sa.local_epoch)
+            sa.state_sharing_priority = self.local_epoch
+            logger.log(self.status_loglevel, f"Transitioning to epoch {self.local_epoch}")
+        self.last_outer_step_seconds = time.perf_counter() - t_start
+
+    def update_main_param_after_outer_step(self) -> None:
+        """No-op kept for API parity: the outer kernel already wrote theta_local (SURVEY.md §2.7 first quirk)."""
+
+    # ------------------------------------------------------------------------------------------ housekeeping
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        self.inner_optimizer.zero_grad(set_to_none=False) if _is_fused(self.inner_optimizer) else \
+            self.inner_optimizer.zero_grad(set_to_none=set_to_none)
+
+    def load_state_from_peers(self, **kwargs) -> None:
+        """Adopt theta_outer / outer state / epoch from the swarm (collective over the outer group; reference:
+        train_fsdp.py:348-349, hivemind_diloco.py:528-531)."""
+        if self.scheduled_diloco_grads is not None:
+            self.scheduled_diloco_grads.cancel()
+            self.scheduled_diloco_grads = None
+        with self.tracker.pause_updates():
+            self.state_averager.load_state_from_peers()
+            self.tracker.report_local_progress(self.local_epoch, samples_accumulated=0)
+
+    def state_dict(self) -> dict:
+        """{"state_dict_outer": outer sd (+ ["state"]["local_epoch"]), "state_dict_inner": inner sd}
+        (hivemind_diloco.py:697-707) plus what the reference forgets to save: theta_outer itself and the inner-step
+        phase."""
+        sd_outer = self.state_averager.optimizer.state_dict()
+        sd_outer["state"]["local_epoch"] = self.local_epoch
+        return {
+            "state_dict_outer": sd_outer,
+            "state_dict_inner": self.inner_optimizer.state_dict(),
+            "theta_outer": self.state_averager.theta_outer.detach().cpu().clone(),
+            "samples_accumulated": self.tracker.local_progress.samples_accumulated,
+        }
+
+    def load_state_dict(self, state_dict: dict) -> None:
+        sd_outer = dict(state_dict["state_dict_outer"])
+        sd_outer["state"] = dict(sd_outer["state"])
+        if "local_epoch" in sd_outer["state"]:
+            self.state_averager.local_epoch = int(sd_outer["state"].pop("local_epoch"))
+        self.state_averager.optimizer.load_state_dict(sd_outer)
+        self.state_averager.reload_optimizer_state()
+        self.inner_optimizer.load_state_dict(state_dict["state_dict_inner"])
+        if state_dict.get("theta_outer") is not None:
+            self.state_averager.theta_outer.copy_(state_dict["theta_outer"])
+        self.tracker.update_epoch(self.local_epoch)
+        self.tracker.report_local_progress(self.local_epoch, int(state_dict.get("samples_accumulated", 0)))
+
+    def shutdown(self) -> None:
+        self.diloco_grad_averager.shutdown()
+        if self._fused is not None:
+            self._fused.close()
+
+
+def _accepts_kw(fn) -> bool:
+    import inspect
+
+    try:
+        sig = inspect.signature(fn)
+    except (TypeError, ValueError):
+        return True
+    return "params" in sig.parameters or any(p.kind == p.VAR_KEYWORD for p in sig.parameters.values())
+
+
+def _is_fused(opt) -> bool:
+    from ..optim.fused import FusedAdamW
+
+    return isinstance(opt, FusedAdamW)

@@ -1,0 +1,112 @@
+"""Model parity on CPU: our hand-scheduled engine vs HF LlamaForCausalLM (the model the reference trains)."""
+import pytest
+import torch
+
+from opendiloco_b200 import LlamaConfig, LlamaForCausalLM
+
+
+def _hf():
+    tr = pytest.importorskip("transformers")
+    return tr
+
+
+def test_matches_hf_llama_fp32(ref_model_dir, tmp_path):
+    tr = _hf()
+    if ref_model_dir is None:
+        cfg = LlamaConfig(hidden_size=64, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2, vocab_size=1024)
+        LlamaForCausalLM(cfg, precision="32-true", seed=1).save_pretrained(str(tmp_path))
+        ref_model_dir = str(tmp_path)
+    torch.manual_seed(0)
+    ours = LlamaForCausalLM.from_pretrained(ref_model_dir, precision="32-true")
+    hf = tr.LlamaForCausalLM.from_pretrained(ref_model_dir, attn_implementation="sdpa").float()
+    ours.train(), hf.train()
+    ids = torch.randint(3, 1024, (2, 48))
+    o1, o2 = ours(input_ids=ids, labels=ids), hf(input_ids=ids, labels=ids)
+    assert abs(o1.loss.item() - o2.loss.item()) < 1e-5
+    o1.loss.backward(), o2.loss.backward()
+    hfp = dict(hf.named_parameters())
+    for n, p in ours.named_parameters():
+        assert torch.allclose(p.grad, hfp[n].grad, atol=2e-6, rtol=1e-4), n
+    assert list(ours.state_dict().keys()) == list(hf.state_dict().keys())
+
+
+def test_gqa_matches_hf(tmp_path):
+    tr = _hf()
+    cfg = LlamaConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=8,
+                      num_key_value_heads=2, vocab_size=512)
+    ours = LlamaForCausalLM(cfg, precision="32-true", seed=3)
+    ours.save_pretrained(str(tmp_path))
+    hf = tr.LlamaForCausalLM.from_pretrained(str(tmp_path)).float()
+    ids = torch.randint(0, 512, (2, 32))
+    labels = ids.clone()
+    labels[0, :5] = -100
+    l1 = ours(input_ids=ids, labels=labels).loss
+    l2 = hf(input_ids=ids, labels=labels).loss
+    assert abs(l1.item() - l2.item()) < 1e-5
+
+
+def test_padding_mask_path_matches_hf(tmp_path):
+    tr = _hf()
+    cfg = LlamaConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=1, num_attention_heads=2, vocab_size=256)
+    ours = LlamaForCausalLM(cfg, precision="32-true", seed=5)
+    ours.save_pretrained(str(tmp_path))
+    hf = tr.LlamaForCausalLM.from_pretrained(str(tmp_path)).float()
+    ids = torch.randint(3, 256, (2, 16))
+    mask = torch.ones_like(ids)
+    mask[1, 10:] = 0                      # right padding
+    labels = ids.clone()
+    labels[mask == 0] = -100
+    l1 = ours(input_ids=ids, attention_mask=mask, labels=labels).loss
+    l2 = hf(input_ids=ids, attention_mask=mask, labels=labels).loss
+    assert abs(l1.item() - l2.item()) < 1e-5
+    l1.backward()
+
+
+def test_native_and_autograd_paths_agree():
+    cfg = LlamaConfig(hidden_size=64, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2, vocab_size=1024)
+    a = LlamaForCausalLM(cfg, precision="bf16-mixed", seed=7)
+    b = LlamaForCausalLM(cfg, precision="bf16-mixed", seed=7)
+    ids = torch.randint(3, 1024, (2, 32))
+    (a(input_ids=ids, labels=ids).loss * 0.25).backward()
+    b.forward_backward(ids, ids, 0.25)
+    assert torch.allclose(a.arena.grad, b.arena.grad, atol=1e-6)
+
+
+def test_bf16_close_to_fp32():
+    cfg = LlamaConfig(hidden_size=64, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2, vocab_size=1024)
+    a = LlamaForCausalLM(cfg, precision="32-true", seed=7)
+    b = LlamaForCausalLM(cfg, precision="bf16-mixed", seed=7)
+    ids = torch.randint(3, 1024, (2, 64))
+    la, lb = a.forward_backward(ids, ids), b.forward_backward(ids, ids)
+    assert abs(la.item() - lb.item()) < 5e-3
+    assert ((a.arena.grad - b.arena.grad).norm() / a.arena.grad.norm()).item() < 2e-2
+
+
+def test_save_load_roundtrip_and_device_api(tmp_path):
+    cfg = LlamaConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=1, num_attention_heads=2, vocab_size=256)
+    a = LlamaForCausalLM(cfg, seed=11)
+    a.save_pretrained(str(tmp_path))
+    b = LlamaForCausalLM.from_pretrained(str(tmp_path))
+    assert torch.equal(a.arena.master, b.arena.master)
+    assert b.to("cpu") is b and b.num_parameters() == sum(p.numel() for p in b.parameters())
+    sd = a.state_dict()
+    c = LlamaForCausalLM(cfg, seed=12)
+    c.load_state_dict(sd)
+    assert torch.equal(c.arena.shadow, a.arena.shadow)
+
+
+def test_activation_hooks_reference_style():
+    """Forward hooks on modules named *self_attn / lm_head fire with something that has .norm() (reference utils.py:25-67)."""
+    from opendiloco_b200.utils.metrics import register_metrics_hooks
+
+    cfg = LlamaConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=2, vocab_size=256)
+    m = LlamaForCausalLM(cfg, precision="32-true", seed=0)
+    log = {}
+    handles = register_metrics_hooks(m, ["self_attn", "lm_head"], log, 1)
+    ids = torch.randint(0, 256, (1, 16))
+    m(input_ids=ids, labels=ids).loss.backward()
+    for h in handles:
+        h.remove()
+    assert set(log) == {"activation/model.layers.0.self_attn", "activation/model.layers.1.self_attn", "activation/lm_head"}
+    full = m(input_ids=ids).logits
+    assert abs(float(log["activation/lm_head"]) - full.float().norm().item()) / full.float().norm().item() < 1e-4
