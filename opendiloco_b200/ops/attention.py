@@ -6,7 +6,8 @@ attention output is written token-major ``[T, Hq*D]`` so it feeds the o-proj GEM
 
 Back-ends:
   * ``tc``     - our tcgen05 kernel (``csrc/attn_sm100.cu``), used when built and the shape qualifies
-  * ``flash``  - flash-attn 2.8 library kernels (BSHD layout, GQA native)
+  * ``cudnn``  - cuDNN fused attention through aten (sm_100 kernels; measured 495/444 TF/s fwd/bwd at B32 S1024 H16 D64)
+  * ``flash``  - flash-attn 2.8 library kernels (sm_80 mma.sync code: 266/196 TF/s on B200), ODB_ATTN_LIB=flash
   * ``math``   - fp32 PyTorch reference (CPU, tests)
 The reference framework itself calls a library here (torch SDPA / flash-attn: train_fsdp.py:107,173).
 """
@@ -18,6 +19,7 @@ import os
 import torch
 
 _FLASH = None
+_LIB = os.environ.get("ODB_ATTN_LIB", "cudnn")
 
 
 def _flash():
@@ -44,6 +46,13 @@ def attention_fwd(qkv: torch.Tensor, B: int, S: int, Hq: int, Hkv: int, D: int):
     q, k, v = split_qkv(qkv, B, S, Hq, Hkv, D)
     scale = 1.0 / math.sqrt(D)
     if qkv.is_cuda and qkv.dtype in (torch.bfloat16, torch.float16):
+        if _LIB == "cudnn":
+            r = torch.ops.aten._scaled_dot_product_cudnn_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), None,
+                                                                   True, 0.0, True, False, scale=scale)
+            out = r[0].transpose(1, 2)          # cuDNN keeps the [B,S,H,D] memory layout of q
+            if not out.is_contiguous():
+                out = out.contiguous()
+            return out.view(B * S, Hq * D), ("cudnn", r)
         out, lse, _, rng = _flash()._flash_attn_forward(q, k, v, 0.0, scale, True, -1, -1, 0.0, None, False)
         return out.view(B * S, Hq * D), (lse, rng)
     # fp32 math reference
@@ -67,6 +76,15 @@ def attention_bwd(dout: torch.Tensor, qkv: torch.Tensor, out: torch.Tensor, aux,
     dq, dk, dv = split_qkv(dqkv, B, S, Hq, Hkv, D)
     scale = 1.0 / math.sqrt(D)
     lse, rng = aux
+    if isinstance(lse, str) and lse == "cudnn":
+        r = rng
+        g = torch.ops.aten._scaled_dot_product_cudnn_attention_backward(
+            dout.view(B, S, Hq, D).transpose(1, 2), q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), r[0], r[1], r[6],
+            r[7], None, r[2], r[3], r[4], r[5], 0.0, True, scale=scale)
+        dq.copy_(g[0].transpose(1, 2))
+        dk.copy_(g[1].transpose(1, 2))
+        dv.copy_(g[2].transpose(1, 2))
+        return dqkv
     if qkv.is_cuda and qkv.dtype in (torch.bfloat16, torch.float16):
         _flash()._flash_attn_backward(dout.view(B, S, Hq, D), q, k, v, out.view(B, S, Hq, D), lse, dq, dk, dv, 0.0, scale,
                                       True, -1, -1, 0.0, None, False, rng)
