@@ -1,0 +1,218 @@
+// K14' - the DiLoCo outer step as ONE kernel over NVLink/NVSwitch peer memory (SURVEY.md §2.5 K14', §5.8).
+//
+// Replaces, per outer step, the reference's 111 x {H2D copy, subtract, NCCL all_reduce} + foreach SGD + 111 D2H copies
+// (train_diloco_torch.py:340-353) and, on the hivemind path, GPU->CPU copies + libp2p butterfly all-reduce + CPU SGD
+// (hivemind_diloco.py:158-167,617-665).
+//
+// Every rank launches the same persistent cooperative grid.  `sym` is this rank's window of a symmetric allocation
+// (same size on every rank, peer-mapped and - when the fabric supports it - bound to a multicast object):
+//
+//   phase 0  delta = theta_outer - theta_local  -> sym (own HBM), fp32 or bf16                    [all CTAs, full vector]
+//   barrier  grid + cross-GPU (flags in a second symmetric window, release/acquire at .sys scope)
+//   phase 1  rank r owns slice r:  mean = (1/N) * sum_p sym_p[slice]     multimem.ld_reduce (in-switch NVLS reduction)
+//            or N peer loads;      sym_p[slice] <- mean for every p       multimem.st (switch multicast) or N peer stores
+//   barrier  grid + cross-GPU
+//   phase 2  buf = mu*buf + mean ; theta_outer -= lr*(mean + mu*buf) ; theta_local = theta_outer ; shadow = bf16(...)
+//
+// i.e. compute -> reduce-scatter -> all-gather -> update, tile by tile over peer memory, in one launch.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+using namespace odb;
+namespace cg = cooperative_groups;
+
+constexpr int kMaxPeers = 16;
+
+struct PeerPtrs {
+  void* p[kMaxPeers];
+};
+
+// ---------------------------------------------------------------------------------------------- multimem PTX
+__device__ __forceinline__ float4 multimem_ld_reduce_f32x4(const void* mc) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(mc) : "memory");
+  return r;
+}
+__device__ __forceinline__ void multimem_st_f32x4(void* mc, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// 8 bf16 values, reduced with fp32 accumulation inside the switch
+__device__ __forceinline__ uint4 multimem_ld_reduce_bf16x8(const void* mc) {
+  uint4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(mc) : "memory");
+  return r;
+}
+__device__ __forceinline__ void multimem_st_bf16x8(void* mc, const uint4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1,%2,%3,%4};"
+               :: "l"(mc), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// loads of data written by other GPUs during this kernel: never served from a stale L1 line
+__device__ __forceinline__ uint4 ld_vol_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ float4 ld_vol_f4(const float* p) {
+  const uint4 r = ld_vol_v4(p);
+  return make_float4(__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w));
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// grid barrier (cooperative) + all-ranks barrier through the flag window.  flags[p][slot*kMaxPeers + r] on rank p is
+// written by rank r.  `seq` increases monotonically across launches so flags never need resetting.
+__device__ __forceinline__ void world_barrier(cg::grid_group& grid, const PeerPtrs& flag_ptrs, int rank, int world,
+                                              unsigned seq, int slot, int* timeout_flag) {
+  __threadfence_system();
+  grid.sync();
+  if (blockIdx.x == 0 && threadIdx.x < world) {
+    const int peer = threadIdx.x;
+    unsigned* remote = reinterpret_cast<unsigned*>(flag_ptrs.p[peer]) + slot * kMaxPeers + rank;
+    st_release_sys(remote, seq);
+    const unsigned* mine = reinterpret_cast<const unsigned*>(flag_ptrs.p[rank]) + slot * kMaxPeers + peer;
+    long long spins = 0;
+    while (ld_acquire_sys(mine) < seq) {
+      if (++spins > (1ll << 31)) {   // ~tens of seconds: a peer is gone; fail loudly instead of hanging the GPU
+        atomicExch(timeout_flag, 1);
+        break;
+      }
+    }
+  }
+  grid.sync();
+  __threadfence_system();
+}
+
+template <bool kBf16Delta, bool kMultimem>
+__global__ void __launch_bounds__(512) fused_outer_kernel(float* __restrict__ theta_outer, float* __restrict__ buf,
+                                                          float* __restrict__ theta_local, __nv_bfloat16* __restrict__ shadow,
+                                                          void* sym_local, void* sym_mc, PeerPtrs sym_peers, PeerPtrs flag_ptrs,
+                                                          int rank, int world, long long n, float lr, float mu, int nesterov,
+                                                          unsigned seq, int* timeout_flag) {
+  cg::grid_group grid = cg::this_grid();
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  constexpr int VEC = kBf16Delta ? 8 : 4;         // elements per 16-byte vector of the delta window
+  const long long nvec = n / VEC;
+
+  // ---------------- phase 0: pseudo-gradient into the local symmetric window
+  for (long long i = tid; i < nvec; i += nthreads) {
+    if constexpr (kBf16Delta) {
+      const float4 a0 = ld_f4(theta_outer + i * 8), a1 = ld_f4(theta_outer + i * 8 + 4);
+      const float4 b0 = ld_f4(theta_local + i * 8), b1 = ld_f4(theta_local + i * 8 + 4);
+      const float d[8] = {a0.x - b0.x, a0.y - b0.y, a0.z - b0.z, a0.w - b0.w, a1.x - b1.x, a1.y - b1.y, a1.z - b1.z, a1.w - b1.w};
+      st_v4(reinterpret_cast<__nv_bfloat16*>(sym_local) + i * 8, pack8(d));
+    } else {
+      const float4 a = ld_f4(theta_outer + i * 4), b = ld_f4(theta_local + i * 4);
+      st_f4(reinterpret_cast<float*>(sym_local) + i * 4, make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w));
+    }
+  }
+  world_barrier(grid, flag_ptrs, rank, world, seq, 0, timeout_flag);
+
+  // ---------------- phase 1: reduce my slice across ranks, publish the mean to every rank
+  const float inv_world = 1.f / (float)world;
+  const long long per = (nvec + world - 1) / world;
+  const long long lo = per * rank, hi = (lo + per < nvec) ? lo + per : nvec;
+  for (long long i = lo + tid; i < hi; i += nthreads) {
+    if constexpr (kMultimem) {
+      if constexpr (kBf16Delta) {
+        const uint4 s = multimem_ld_reduce_bf16x8(reinterpret_cast<const __nv_bfloat16*>(sym_mc) + i * 8);
+        float f[8];
+        unpack8(s, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] *= inv_world;
+        multimem_st_bf16x8(reinterpret_cast<__nv_bfloat16*>(sym_mc) + i * 8, pack8(f));
+      } else {
+        float4 s = multimem_ld_reduce_f32x4(reinterpret_cast<const float*>(sym_mc) + i * 4);
+        s.x *= inv_world; s.y *= inv_world; s.z *= inv_world; s.w *= inv_world;
+        multimem_st_f32x4(reinterpret_cast<float*>(sym_mc) + i * 4, s);
+      }
+    } else {
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int p = 0; p < world; ++p) {
+        const int src = (rank + p) % world;          // stagger peers so the links are used evenly
+        if constexpr (kBf16Delta) {
+          float f[8];
+          unpack8(ld_vol_v4(reinterpret_cast<const __nv_bfloat16*>(sym_peers.p[src]) + i * 8), f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        } else {
+          const float4 v = ld_vol_f4(reinterpret_cast<const float*>(sym_peers.p[src]) + i * 4);
+          acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] *= inv_world;
+      for (int p = 0; p < world; ++p) {
+        const int dst = (rank + p) % world;
+        if constexpr (kBf16Delta) st_v4(reinterpret_cast<__nv_bfloat16*>(sym_peers.p[dst]) + i * 8, pack8(acc));
+        else st_f4(reinterpret_cast<float*>(sym_peers.p[dst]) + i * 4, make_float4(acc[0], acc[1], acc[2], acc[3]));
+      }
+    }
+  }
+  world_barrier(grid, flag_ptrs, rank, world, seq + 1, 1, timeout_flag);
+
+  // ---------------- phase 2: SGD-Nesterov on the whole vector from the (now averaged) local window
+  for (long long i = tid; i < n / 4; i += nthreads) {
+    float4 d;
+    if constexpr (kBf16Delta) {
+      uint2 u;
+      asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(u.x), "=r"(u.y)
+                   : "l"(reinterpret_cast<const __nv_bfloat16*>(sym_local) + i * 4) : "memory");
+      const float2 a = bf2_to_f2(u.x), b = bf2_to_f2(u.y);
+      d = make_float4(a.x, a.y, b.x, b.y);
+    } else {
+      d = ld_vol_f4(reinterpret_cast<const float*>(sym_local) + i * 4);
+    }
+    float4 to = ld_f4(theta_outer + i * 4), bb = ld_f4(buf + i * 4);
+    float* T = &to.x; float* B = &bb.x; const float* D = &d.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      B[j] = mu * B[j] + D[j];
+      const float stp = nesterov ? (D[j] + mu * B[j]) : B[j];
+      T[j] -= lr * stp;
+    }
+    st_f4(theta_outer + i * 4, to);
+    st_f4(buf + i * 4, bb);
+    st_f4(theta_local + i * 4, to);
+    if (shadow) *reinterpret_cast<uint2*>(shadow + i * 4) = make_uint2(f2_to_bf2(to.x, to.y), f2_to_bf2(to.z, to.w));
+  }
+}
+
+// n must be a multiple of 8*world (flat arenas are padded to 16384).  Returns 0, a cudaError, or -3 if co-residency fails.
+ODB_EXPORT int odb_fused_outer_step(void* theta_outer, void* buf, void* theta_local, void* shadow, void* sym_local,
+                                    void* sym_mc, const void* const* sym_peers, const void* const* flag_ptrs, int rank,
+                                    int world, long long n, float lr, float mu, int nesterov, unsigned seq, int delta_bf16,
+                                    void* timeout_flag, cudaStream_t st) {
+  if (world > kMaxPeers || n % (8ll * world)) return -1;
+  PeerPtrs sp{}, fp{};
+  for (int i = 0; i < world; ++i) {
+    sp.p[i] = const_cast<void*>(sym_peers[i]);
+    fp.p[i] = const_cast<void*>(flag_ptrs[i]);
+  }
+  const bool mm = sym_mc != nullptr;
+  void* fn;
+  if (delta_bf16) fn = mm ? (void*)fused_outer_kernel<true, true> : (void*)fused_outer_kernel<true, false>;
+  else fn = mm ? (void*)fused_outer_kernel<false, true> : (void*)fused_outer_kernel<false, false>;
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 512, 0);
+  if (e != cudaSuccess) return (int)e;
+  if (per_sm < 1) return -3;
+  const int grid = sm_count() * (per_sm > 2 ? 2 : per_sm);
+  float* a0 = (float*)theta_outer; float* a1 = (float*)buf; float* a2 = (float*)theta_local;
+  __nv_bfloat16* a3 = (__nv_bfloat16*)shadow; int* tf = (int*)timeout_flag;
+  void* args[] = {&a0, &a1, &a2, &a3, &sym_local, &sym_mc, &sp, &fp, &rank, &world, &n, &lr, &mu, &nesterov, &seq, &tf};
+  e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(512), args, 0, st);
+  return (int)e;
+}

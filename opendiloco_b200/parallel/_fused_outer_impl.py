@@ -1,0 +1,101 @@
+"""Host side of the fused outer step (``csrc/outer_comm.cu``): NVLink symmetric-memory windows + launch.
+
+``torch.distributed._symmetric_memory`` is used purely as plumbing: it allocates the same-sized window on every rank of
+the outer group, exchanges the handles, maps every peer's window into this process (P2P over NVLink 5) and - when the
+fabric supports NVLS - binds them to one multicast address.  The kernel that touches those pointers is ours.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+import torch.distributed as dist
+
+from .. import _lib
+from ..utils.logger import get_logger
+
+c_void_p, c_int, c_ll, c_float, c_uint = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_uint
+_lib.register_optional("odb_fused_outer_step", [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                c_int, c_int, c_ll, c_float, c_float, c_int, c_uint, c_int, c_void_p, c_void_p])
+logger = get_logger()
+FLAG_WORDS = 64     # 2 barrier slots x 16 peers, padded
+
+
+class FusedOuterStep:
+    """pseudo-gradient -> (bf16 cast) -> NVLink all-reduce -> Nesterov -> theta_local/shadow write-back: one launch."""
+
+    def __init__(self, opt, group, delta_bf16: bool):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        sa = opt.state_averager
+        self.opt, self.sa, self.group = opt, sa, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.n = sa.theta_outer.numel()
+        assert self.n % (8 * self.world) == 0
+        dev = sa.theta_outer.device
+        self.delta_bf16 = delta_bf16
+        dt = torch.bfloat16 if delta_bf16 else torch.float32
+        self.window = symm_mem.empty(self.n, dtype=dt, device=dev)
+        self.flags = symm_mem.empty(FLAG_WORDS, dtype=torch.int32, device=dev)
+        self.flags.zero_()
+        gname = group.group_name
+        try:
+            if hasattr(symm_mem, "is_symm_mem_enabled_for_group") and not symm_mem.is_symm_mem_enabled_for_group(gname):
+                symm_mem.enable_symm_mem_for_group(gname)
+        except Exception:
+            pass
+        self.h_win = symm_mem.rendezvous(self.window, gname)
+        self.h_flag = symm_mem.rendezvous(self.flags, gname)
+        self.mc_ptr = int(getattr(self.h_win, "multicast_ptr", 0) or 0)
+        if os.environ.get("ODB_FUSED_OUTER_NO_MULTIMEM"):
+            self.mc_ptr = 0
+        PtrArr = c_void_p * self.world
+        self._win_ptrs = PtrArr(*[int(p) for p in self.h_win.buffer_ptrs])
+        self._flag_ptrs = PtrArr(*[int(p) for p in self.h_flag.buffer_ptrs])
+        self.timeout_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.seq = 1
+        torch.cuda.synchronize(dev)
+        self.h_flag.barrier()
+        logger.info(f"fused outer step: {self.world} ranks, window {self.n * self.window.element_size() / 1e6:.0f} MB "
+                    f"{'bf16' if delta_bf16 else 'fp32'}, multimem={'yes' if self.mc_ptr else 'no (P2P loads/stores)'}")
+
+    @classmethod
+    def try_create(cls, opt, compression=None):
+        dht = opt.dht
+        if dht is None or dht.group is None or not torch.cuda.is_available():
+            return None
+        if dist.get_backend(dht.group) != "nccl" or not _lib.has_symbol("odb_fused_outer_step"):
+            return None
+        sa = opt.state_averager
+        g = sa._sgd_hparams()
+        if g is None or g.get("momentum", 0) == 0 or sa.theta_outer.device != sa.theta_local.device:
+            return None
+        bf16 = compression is not None and getattr(compression, "name", "") == "bf16"
+        try:
+            return cls(opt, dht.group, bf16)
+        except Exception as e:  # symmetric memory unavailable (no P2P, driver too old, ...): NCCL path is used instead
+            logger.warning(f"fused outer step unavailable ({type(e).__name__}: {e}); using flat NCCL all-reduce + fused Nesterov")
+            return None
+
+    @torch.no_grad()
+    def outer_step(self) -> None:
+        sa = self.sa
+        g = sa._sgd_hparams()
+        lib = _lib.cuda_lib()
+        rc = lib.odb_fused_outer_step(
+            sa.theta_outer.data_ptr(), sa.momentum_buffer.data_ptr(), sa.theta_local.data_ptr(),
+            sa.shadow_local.data_ptr() if sa.shadow_local is not None else None, self.window.data_ptr(),
+            self.mc_ptr if self.mc_ptr else None, self._win_ptrs, self._flag_ptrs, self.rank, self.world, self.n,
+            float(g["lr"]), float(g["momentum"]), int(bool(g.get("nesterov", False))), self.seq, int(self.delta_bf16),
+            self.timeout_flag.data_ptr(), _lib.stream_ptr(sa.theta_outer))
+        _lib.check(rc, "fused_outer_step")
+        _lib.count_launch()
+        self.seq += 2
+        sa.fv.gather_compute_weights()
+
+    def check_timeout(self) -> bool:
+        return bool(self.timeout_flag.item())
+
+    def close(self) -> None:
+        self.window = self.flags = None
