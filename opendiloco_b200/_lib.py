@@ -50,6 +50,10 @@ _OPTIONAL_SIGS: dict[str, list] = {}
 
 def register_optional(name: str, argtypes: list) -> None:
     _OPTIONAL_SIGS[name] = argtypes
+    if _cuda is not None and hasattr(_cuda, name):     # library already loaded: bind the prototype now
+        fn = getattr(_cuda, name)
+        fn.argtypes = argtypes
+        fn.restype = c_int
 
 
 class NativeLibraryMissing(RuntimeError):
