@@ -124,21 +124,47 @@ __global__ void __launch_bounds__(512) fused_outer_kernel(float* __restrict__ th
   const float inv_world = 1.f / (float)world;
   const long long per = (nvec + world - 1) / world;
   const long long lo = per * rank, hi = (lo + per < nvec) ? lo + per : nvec;
-  for (long long i = lo + tid; i < hi; i += nthreads) {
-    if constexpr (kMultimem) {
+  if constexpr (kMultimem) {
+    // 4 independent in-switch reductions in flight per thread before the dependent multicast stores
+    constexpr int U = 4;
+    for (long long i0 = lo + tid; i0 < hi; i0 += nthreads * U) {
       if constexpr (kBf16Delta) {
-        const uint4 s = multimem_ld_reduce_bf16x8(reinterpret_cast<const __nv_bfloat16*>(sym_mc) + i * 8);
-        float f[8];
-        unpack8(s, f);
+        uint4 s[U];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] *= inv_world;
-        multimem_st_bf16x8(reinterpret_cast<__nv_bfloat16*>(sym_mc) + i * 8, pack8(f));
+        for (int u = 0; u < U; ++u) {
+          const long long i = i0 + u * nthreads;
+          if (i < hi) s[u] = multimem_ld_reduce_bf16x8(reinterpret_cast<const __nv_bfloat16*>(sym_mc) + i * 8);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const long long i = i0 + u * nthreads;
+          if (i < hi) {
+            float f[8];
+            unpack8(s[u], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] *= inv_world;
+            multimem_st_bf16x8(reinterpret_cast<__nv_bfloat16*>(sym_mc) + i * 8, pack8(f));
+          }
+        }
       } else {
-        float4 s = multimem_ld_reduce_f32x4(reinterpret_cast<const float*>(sym_mc) + i * 4);
-        s.x *= inv_world; s.y *= inv_world; s.z *= inv_world; s.w *= inv_world;
-        multimem_st_f32x4(reinterpret_cast<float*>(sym_mc) + i * 4, s);
+        float4 s[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const long long i = i0 + u * nthreads;
+          if (i < hi) s[u] = multimem_ld_reduce_f32x4(reinterpret_cast<const float*>(sym_mc) + i * 4);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const long long i = i0 + u * nthreads;
+          if (i < hi) {
+            s[u].x *= inv_world; s[u].y *= inv_world; s[u].z *= inv_world; s[u].w *= inv_world;
+            multimem_st_f32x4(reinterpret_cast<float*>(sym_mc) + i * 4, s[u]);
+          }
+        }
       }
-    } else {
+    }
+  } else {
+    for (long long i = lo + tid; i < hi; i += nthreads) {
       float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       for (int p = 0; p < world; ++p) {
         const int src = (rank + p) % world;          // stagger peers so the links are used evenly

@@ -10,6 +10,7 @@ values (ints, floats, Literals, enums, ``str | bool | None``) is pydantic's.
 """
 from __future__ import annotations
 
+import re
 import sys
 from typing import Any
 
@@ -24,7 +25,14 @@ def _norm(key: str) -> str:
     return key.replace("-", "_")
 
 
+_INT_WITH_UNDERSCORES = re.compile(r"^[+-]?\d+(_\d+)+$")
+
+
 def _set(d: dict, dotted: str, value: Any) -> None:
+    if isinstance(value, str) and _INT_WITH_UNDERSCORES.match(value):
+        value = value.replace("_", "")          # 88_000 (R/README.md:122)
+    if isinstance(value, str) and value.lower() in ("true", "false"):
+        value = value.lower() == "true"
     parts = [_norm(p) for p in dotted.split(".")]
     for p in parts[:-1]:
         d = d.setdefault(p, {})

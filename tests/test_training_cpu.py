@@ -1,0 +1,95 @@
+"""Integration tests of the CLI entry points on CPU/gloo (torchrun, world_size 2), mirroring the reference's
+tests/test_training/test_train.py: checkpoint/resume loss-curve continuity for the plain data-parallel path (atol 1e-3)
+and for 2 DiLoCo workers (atol 1e-2), plus the train_diloco_torch entry (BASELINE.json config #1)."""
+import os
+import pickle
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def free_port() -> int:
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def torchrun(nproc: int, module: str, args: list[str], timeout: int = 900) -> None:
+    env = dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2", WANDB_MODE="disabled")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+           "--master-port", str(free_port()), "-m", module, *args]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout)
+    if res.returncode != 0:
+        pytest.fail(f"{' '.join(cmd)}\n{res.stdout[-3000:]}\n{res.stderr[-3000:]}")
+
+
+BASE = ["--path_model", "2m", "--fake_data", "--no-torch_compile", "--lr", "1e-2", "--per_device_train_batch_size", "4",
+        "--total_batch_size", "16", "--seq_length", "64", "--metric_logger_type", "dummy", "--precision", "bf16-mixed",
+        "--warmup_steps", "4", "--total_steps", "100"]
+
+
+def _load(path):
+    with open(path, "rb") as f:
+        return {d["step"]: (d["Loss"], d["lr"]) for d in pickle.load(f)}
+
+
+@pytest.mark.parametrize("sharding", ["NO_SHARD", "SHARD_GRAD_OP"])
+def test_ckpt_resume_data_parallel(tmp_path, sharding):
+    ckpt = f"{tmp_path}/ckpt"
+    log1, log2 = f"{tmp_path}/log1.pkl", f"{tmp_path}/log2.pkl"
+    common = BASE + ["--max_steps", "12", "--sharding_strategy", sharding]
+    torchrun(2, "opendiloco_b200.train_fsdp", common + ["--ckpt.path", ckpt, "--ckpt.interval", "4", "--project", log1])
+    assert os.path.isfile(f"{ckpt}/model_step_8/global_state_dict.pt") and os.path.isfile(f"{ckpt}/model_step_8/.metadata")
+    torchrun(2, "opendiloco_b200.train_fsdp", common + ["--ckpt.path", ckpt, "--ckpt.resume", f"{ckpt}/model_step_8", "--project", log2])
+    a, b = _load(log1), _load(log2)
+    common_steps = set(a) & set(b)
+    assert common_steps == {9, 10, 11, 12}
+    for s in common_steps:
+        assert np.allclose(a[s][0], b[s][0], atol=1e-3), f"Loss at step {s} is different: {a[s][0]} vs {b[s][0]}"
+        assert a[s][1] == b[s][1], f"Lr at step {s} is different"
+
+
+def test_ckpt_resume_two_diloco_workers(tmp_path):
+    """2 DiLoCo workers x 1 rank, H=5, resume from a step that is NOT a multiple of H (the reference silently moves the
+    outer anchor in that case; we restore theta_outer and the inner-step phase)."""
+    ckpt = f"{tmp_path}/ckpt"
+    log1, log2 = f"{tmp_path}/log1.pkl", f"{tmp_path}/log2.pkl"
+    hv = ["--hv.local_steps", "5", "--hv.galaxy_size", "2", "--hv.skip_load_from_peers", "--hv.fail_rank_drop", "--hv.matchmaking_time", "1",
+          "--total_batch_size", "8", "--max_steps", "16"]
+    torchrun(2, "opendiloco_b200.train_fsdp", BASE + hv + ["--ckpt.path", ckpt, "--ckpt.interval", "7", "--project", log1])
+    assert os.path.isdir(f"{ckpt}/model_step_7/diloco_rank_0") and os.path.isdir(f"{ckpt}/model_step_7/diloco_rank_1")
+    torchrun(2, "opendiloco_b200.train_fsdp", BASE + hv + ["--ckpt.path", ckpt, "--ckpt.resume", f"{ckpt}/model_step_7", "--project", log2])
+    a, b = _load(log1), _load(log2)
+    common_steps = set(a) & set(b)
+    assert common_steps == set(range(8, 17))
+    for s in common_steps:
+        assert np.allclose(a[s][0], b[s][0], atol=1e-2), f"Loss at step {s} is different: {a[s][0]} vs {b[s][0]}"
+        assert a[s][1] == b[s][1]
+
+
+def test_resume_latest_and_topk(tmp_path):
+    ckpt = f"{tmp_path}/ckpt"
+    args = BASE + ["--max_steps", "6", "--ckpt.path", ckpt, "--ckpt.interval", "2", "--ckpt.topk", "2", "--project", f"{tmp_path}/l.pkl"]
+    torchrun(1, "opendiloco_b200.train_fsdp", args)
+    assert sorted(os.listdir(ckpt)) == ["model_step_4", "model_step_6"]
+    torchrun(1, "opendiloco_b200.train_fsdp", BASE + ["--max_steps", "8", "--ckpt.path", ckpt, "--ckpt.resume", "--project", f"{tmp_path}/l2.pkl"])
+    assert min(_load(f"{tmp_path}/l2.pkl")) == 7
+
+
+def test_train_diloco_torch_two_workers_gloo(tmp_path):
+    """BASELINE.json config #1 in miniature: train_diloco_torch, 2 workers, local_steps=3, CPU/gloo."""
+    log = f"{tmp_path}/log.pkl"
+    torchrun(2, "opendiloco_b200.train_diloco_torch",
+             ["--model-name-or-path", "2m", "--fake-data", "--batch-size", "8", "--per-device-train-batch-size", "4", "--seq-length", "64",
+              "--local-steps", "3", "--max-steps", "7", "--lr", "1e-2", "--warmup-steps", "2", "--total-steps", "50",
+              "--metric-logger-type", "dummy", "--project", log, "--checkpoint-interval", "6", "--checkpoint-path", f"{tmp_path}/out",
+              "--eval-steps", "4", "--log-activations-steps", "5"])
+    m = pickle.load(open(log, "rb"))
+    assert [d["step"] for d in m] == list(range(1, 8))
+    assert m[-1]["effective_step"] == 14 and "eval_loss" in m[3] and any(k.startswith("activation/") for k in m[4])
+    assert all(np.isfinite(d["Loss"]) for d in m)
