@@ -1,0 +1,158 @@
+"""DiLoCoOptimizer / averager / tracker semantics (CPU).  Oracle = the reference's 14-line torch loop
+(train_diloco_torch.py:336-353); API checks mirror tests/test_diloco_hivemind.py of the reference."""
+import copy
+import os
+import subprocess
+import sys
+from functools import partial
+
+import pytest
+import torch
+
+from opendiloco_b200 import AllReduceStrategy, DiLoCoGradAverager, DiLoCoOptimizer, FusedAdamW
+from opendiloco_b200.parallel.diloco import DiloCoProgressTracker
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _oracle(model, data, H, steps, lr=1e-2):
+    inner = torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=0.1, betas=(0.9, 0.95))
+    outer = torch.optim.SGD(model.parameters(), lr=0.7, momentum=0.9, nesterov=True)
+    off = [p.data.clone() for p in model.parameters()]
+    for s in range(1, steps + 1):
+        x, y = data[s - 1]
+        torch.nn.functional.mse_loss(model(x), y).backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        inner.step()
+        inner.zero_grad()
+        if s % H == 0:
+            for po, p in zip(off, model.parameters()):
+                p.grad = po - p.data
+                p.data = po
+            outer.step()
+            outer.zero_grad()
+            off = [p.data.clone() for p in model.parameters()]
+    return [p.data.clone() for p in model.parameters()]
+
+
+def _mlp():
+    torch.manual_seed(0)
+    return torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(), torch.nn.Linear(16, 1))
+
+
+def _opt(model, H=4, inner=None, **kw):
+    inner = inner or partial(FusedAdamW, lr=1e-2, weight_decay=0.1, betas=(0.9, 0.95), max_grad_norm=1.0)
+    return DiLoCoOptimizer(batch_size=32, num_inner_steps=H, params=model.parameters(),
+                           outer_optimizer=partial(torch.optim.SGD, lr=0.7, momentum=0.9, nesterov=True), inner_optimizer=inner, **kw)
+
+
+@pytest.mark.parametrize("inner_kind", ["fused", "torch"])
+def test_solo_outer_step_matches_reference_loop(inner_kind):
+    m1 = _mlp()
+    m2 = copy.deepcopy(m1)
+    data = [(torch.randn(32, 8), torch.randn(32, 1)) for _ in range(12)]
+    ref = _oracle(m1, data, 4, 12)
+    if inner_kind == "fused":
+        opt = _opt(m2)
+    else:
+        opt = _opt(m2, inner=partial(torch.optim.AdamW, lr=1e-2, weight_decay=0.1, betas=(0.9, 0.95)))
+    for s in range(12):
+        x, y = data[s]
+        torch.nn.functional.mse_loss(m2(x), y).backward()
+        if inner_kind == "torch":
+            torch.nn.utils.clip_grad_norm_(m2.parameters(), 1.0)
+        opt.step()
+        opt.zero_grad()
+    assert opt.local_epoch == 3 and opt.tracker.local_progress.samples_accumulated == 0
+    for a, b in zip(ref, m2.parameters()):
+        assert torch.allclose(a, b.data, atol=1e-6)
+
+
+def test_state_dict_roundtrip():
+    """Mirrors test_load_and_save_state of the reference (tests/test_diloco_hivemind.py:99-151)."""
+    m = _mlp()
+    sched = partial(torch.optim.lr_scheduler.StepLR, gamma=0.5, step_size=1)
+    o1 = _opt(m, H=5, scheduler=sched, matchmaking_time=1.0, averaging_timeout=5.0, verbose=False)
+    for _ in range(7):
+        torch.nn.functional.mse_loss(m(torch.randn(32, 8)), torch.randn(32, 1)).backward()
+        o1.step()
+        o1.zero_grad()
+    sd = o1.state_dict()
+    assert set(sd) >= {"state_dict_outer", "state_dict_inner"} and sd["state_dict_outer"]["state"]["local_epoch"] == 1
+    o2 = _opt(_mlp(), H=5, scheduler=sched)
+    o2.load_state_dict(sd)
+    sd2 = o2.state_dict()
+    assert o2.local_epoch == 1 and o2.tracker.local_progress.samples_accumulated == 64
+    assert o1.state_averager.optimizer.param_groups[0]["lr"] == o2.state_averager.optimizer.param_groups[0]["lr"]
+    for k, st in sd["state_dict_outer"]["state"].items():
+        if k != "local_epoch":
+            assert torch.equal(st["momentum_buffer"], sd2["state_dict_outer"]["state"][k]["momentum_buffer"])
+    for k, st in sd["state_dict_inner"]["state"].items():
+        assert torch.equal(st["exp_avg"], sd2["state_dict_inner"]["state"][k]["exp_avg"])
+    assert torch.equal(sd["theta_outer"], sd2["theta_outer"])
+    assert o1.state_averager.inner_optimizer is o1.inner_optimizer and o1.param_groups is o1.inner_optimizer.param_groups
+
+
+def test_constructor_validation():
+    m = _mlp()
+    with pytest.raises(KeyError):
+        _opt(m, optimizer=torch.optim.SGD)
+    with pytest.raises(KeyError):
+        _opt(m, target_batch_size=4)
+    with pytest.raises(KeyError):
+        _opt(m, batch_size_per_step=4)
+    with pytest.raises(ValueError):
+        _opt(m, use_local_updates=False)
+    with pytest.raises(ValueError):
+        _opt(m, offload_optimizer=False)
+    with pytest.raises(ValueError):
+        _opt(m, delay_optimizer_step=True)
+    with pytest.raises(ValueError):
+        _opt(m, all_reduce_strategy=AllReduceStrategy.NO_WAIT, timeout_waiting_for_peers=10.0)
+    with pytest.raises(ValueError):
+        _opt(m, timeout_waiting_for_peers=1.0, matchmaking_time=15.0)
+    with pytest.raises(TypeError):
+        DiLoCoOptimizer(batch_size=1, num_inner_steps=1, params=m.parameters(), outer_optimizer=torch.optim.SGD(m.parameters(), lr=1),
+                        inner_optimizer=partial(torch.optim.AdamW))
+    o = _opt(m, use_local_updates=True, offload_optimizer=True, delay_grad_averaging=False)
+    assert o.timeout_waiting_for_peers == 600 and o.tracker.global_progress.num_peers == 1
+    assert AllReduceStrategy("NO_WAIT") is AllReduceStrategy.NO_WAIT
+
+
+def test_progress_tracker_semantics():
+    t = DiloCoProgressTracker(batch_size=8, num_inner_steps=5)
+    assert t.target_batch_size == 40 and not t.ready_to_update_epoch
+    for i in range(1, 6):
+        t.report_local_progress(0, 8 * i)
+    assert t.ready_to_update_epoch and t.local_step == 5 and t.estimated_next_update_time == 0.0
+    t.update_epoch(1)
+    assert t.local_progress.samples_accumulated == 0 and t.global_epoch == 1 and t.real_step == 5   # epoch * H (not * batch: SURVEY §2.7)
+    with t.pause_updates():
+        pass
+
+
+def test_grad_averager_standalone_api():
+    """DiLoCoGradAverager on arbitrary (non-flat) parameters, solo swarm (reference test :53-96 uses 4 peers over a DHT)."""
+    main, off = torch.nn.Linear(5, 1, bias=False), torch.nn.Linear(5, 1, bias=False)
+    opt = torch.optim.SGD(off.parameters(), lr=0.1)
+    with pytest.raises(ValueError):
+        DiLoCoGradAverager(main_parameters=main.parameters(), offloaded_optimizer=opt, dht=None, prefix="g")
+    with pytest.raises(KeyError):
+        DiLoCoGradAverager(main_parameters=tuple(main.parameters()), offloaded_optimizer=opt, dht=None, prefix="g", client_mode=True)
+    av = DiLoCoGradAverager(main_parameters=tuple(main.parameters()), offloaded_optimizer=opt, dht=None, prefix="g",
+                            client_mode=False, auxiliary=False, start=True, target_group_size=4, min_matchmaking_time=1)
+    ctrl = av.step(wait=False)
+    assert av.peer_id in ctrl.result()
+    with av.get_tensors() as grads:
+        assert torch.allclose(grads[0], off.weight.data - main.weight.data) and not torch.isnan(grads[0]).any()
+    av.shutdown()
+
+
+def test_multi_worker_equivalence_gloo():
+    """2 workers over gloo: flat collective + every compression codec against the simulated-swarm oracle."""
+    env = dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29613", os.path.join(ROOT, "tests", "dist_workers", "outer_equiv.py")]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "FAIL" not in res.stdout and res.stdout.count("OK") >= 7
