@@ -1,0 +1,58 @@
+"""Python front-end of the tcgen05 GEMM family (``csrc/gemm_sm100.cu``).
+
+``linear``         y = x @ W^T                                  (bf16 in/out, fp32 accumulate in TMEM)
+``linear_swiglu``  gu = x @ Wgu^T ; act = silu(gate) * up        (one kernel: the SwiGLU pass is the GEMM epilogue)
+``linear_qkv_rope`` qkv = x @ Wqkv^T with RoPE on the q|k heads   (RoPE is the GEMM epilogue; head_dim 64)
+
+All three require CUDA bf16 tensors with contiguous rows; callers fall back to the library GEMM + stand-alone kernels
+for other dtypes/devices (CPU tests, fp32 runs)."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+from .. import _lib
+
+c_void_p, c_int, c_ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong
+_lib.register_optional("odb_gemm_bf16_tn", [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_void_p])
+_lib.register_optional("odb_gemm_swiglu", [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p])
+_lib.register_optional("odb_gemm_qkv_rope", [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p])
+
+ENABLED = os.environ.get("ODB_TC_GEMM", "1") != "0"
+
+
+def usable(*tensors: torch.Tensor) -> bool:
+    return ENABLED and all(t.is_cuda and t.dtype == torch.bfloat16 and t.stride(-1) == 1 for t in tensors) and \
+        _lib.has_symbol("odb_gemm_bf16_tn")
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    M, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(M, N, dtype=x.dtype, device=x.device)
+    _lib.check(_lib.cuda_lib().odb_gemm_bf16_tn(x.data_ptr(), w.data_ptr(), out.data_ptr(), M, N, K, x.stride(0), w.stride(0),
+                                                out.stride(0), _lib.stream_ptr(x)), "gemm_bf16_tn")
+    _lib.count_launch()
+    return out
+
+
+def linear_swiglu(x: torch.Tensor, w_gu: torch.Tensor, gu: torch.Tensor, act: torch.Tensor) -> None:
+    M, K = x.shape
+    I = w_gu.shape[0] // 2
+    assert x.is_contiguous() and w_gu.is_contiguous() and gu.is_contiguous() and act.is_contiguous()
+    _lib.check(_lib.cuda_lib().odb_gemm_swiglu(x.data_ptr(), w_gu.data_ptr(), gu.data_ptr(), act.data_ptr(), M, I, K,
+                                               _lib.stream_ptr(x)), "gemm_swiglu")
+    _lib.count_launch()
+
+
+def linear_qkv_rope(x: torch.Tensor, w: torch.Tensor, qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, S: int,
+                    rope_cols: int) -> None:
+    M, K = x.shape
+    N = w.shape[0]
+    assert x.is_contiguous() and w.is_contiguous() and qkv.is_contiguous() and cos.shape[1] == 32
+    _lib.check(_lib.cuda_lib().odb_gemm_qkv_rope(x.data_ptr(), w.data_ptr(), qkv.data_ptr(), M, N, K, S, rope_cols, cos.data_ptr(),
+                                                 sin.data_ptr(), _lib.stream_ptr(x)), "gemm_qkv_rope")
+    _lib.count_launch()
