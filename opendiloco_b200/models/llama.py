@@ -25,6 +25,7 @@ from torch import nn
 from ..ops import attention as A
 from ..ops import gemm as G
 from ..ops import kernels as K
+from ..ops import tc_gemm as TC
 from .arena import ParamArena, hf_param_order
 from .config import LlamaConfig
 
@@ -122,8 +123,12 @@ class LlamaEngine:
             # --- attention block:  xa = x_prev + delta ; xn1 = norm(xa)
             K.rmsnorm_fwd(x_prev, ar.w(p + "input_layernorm.weight"), cfg.rms_norm_eps, delta=delta, out=ws.xn1[l],
                           rstd=ws.rstd1[l], x_out=ws.xa[l])
-            G.mm_nt(ws.xn1[l], ar.qkv_w(l), out=ws.qkv[l])
-            K.rope_(ws.qkv[l], ws.cos, ws.sin, S, Hq + Hkv, D)
+            if D == 64 and TC.usable(ws.xn1[l], ar.qkv_w(l)):
+                # tcgen05 GEMM with the rotary embedding applied in the epilogue (no separate RoPE pass over q|k)
+                TC.linear_qkv_rope(ws.xn1[l], ar.qkv_w(l), ws.qkv[l], ws.cos, ws.sin, S, (Hq + Hkv) * D)
+            else:
+                G.mm_nt(ws.xn1[l], ar.qkv_w(l), out=ws.qkv[l])
+                K.rope_(ws.qkv[l], ws.cos, ws.sin, S, Hq + Hkv, D)
             if attention_mask is None:
                 ws.att[l], ws.aux[l] = A.attention_fwd(ws.qkv[l], B, S, Hq, Hkv, D)
             else:
