@@ -20,7 +20,16 @@ _lib.register_optional("odb_gemm_bf16_tn", [c_void_p, c_void_p, c_void_p, c_int,
 _lib.register_optional("odb_gemm_swiglu", [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p])
 _lib.register_optional("odb_gemm_qkv_rope", [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p])
 
+for _n in ("odb_gemm2_bf16_tn", "odb_gemm2_swiglu", "odb_gemm2_qkv_rope"):
+    _lib.register_optional(_n, _lib._OPTIONAL_SIGS[_n.replace("gemm2", "gemm")])
+
 ENABLED = os.environ.get("ODB_TC_GEMM", "1") != "0"
+TWO_CTA = os.environ.get("ODB_TC_GEMM_2CTA", "1") != "0"     # CTA-pair (cta_group::2, 256x256 tiles) kernels
+
+
+def _fn(name: str):
+    lib = _lib.cuda_lib()
+    return getattr(lib, name.replace("odb_gemm_", "odb_gemm2_") if TWO_CTA else name)
 
 
 def usable(*tensors: torch.Tensor) -> bool:
@@ -33,7 +42,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor | None = None) ->
     N = w.shape[0]
     if out is None:
         out = torch.empty(M, N, dtype=x.dtype, device=x.device)
-    _lib.check(_lib.cuda_lib().odb_gemm_bf16_tn(x.data_ptr(), w.data_ptr(), out.data_ptr(), M, N, K, x.stride(0), w.stride(0),
+    _lib.check(_fn("odb_gemm_bf16_tn")(x.data_ptr(), w.data_ptr(), out.data_ptr(), M, N, K, x.stride(0), w.stride(0),
                                                 out.stride(0), _lib.stream_ptr(x)), "gemm_bf16_tn")
     _lib.count_launch()
     return out
@@ -43,7 +52,7 @@ def linear_swiglu(x: torch.Tensor, w_gu: torch.Tensor, gu: torch.Tensor, act: to
     M, K = x.shape
     I = w_gu.shape[0] // 2
     assert x.is_contiguous() and w_gu.is_contiguous() and gu.is_contiguous() and act.is_contiguous()
-    _lib.check(_lib.cuda_lib().odb_gemm_swiglu(x.data_ptr(), w_gu.data_ptr(), gu.data_ptr(), act.data_ptr(), M, I, K,
+    _lib.check(_fn("odb_gemm_swiglu")(x.data_ptr(), w_gu.data_ptr(), gu.data_ptr(), act.data_ptr(), M, I, K,
                                                _lib.stream_ptr(x)), "gemm_swiglu")
     _lib.count_launch()
 
@@ -53,6 +62,6 @@ def linear_qkv_rope(x: torch.Tensor, w: torch.Tensor, qkv: torch.Tensor, cos: to
     M, K = x.shape
     N = w.shape[0]
     assert x.is_contiguous() and w.is_contiguous() and qkv.is_contiguous() and cos.shape[1] == 32
-    _lib.check(_lib.cuda_lib().odb_gemm_qkv_rope(x.data_ptr(), w.data_ptr(), qkv.data_ptr(), M, N, K, S, rope_cols, cos.data_ptr(),
+    _lib.check(_fn("odb_gemm_qkv_rope")(x.data_ptr(), w.data_ptr(), qkv.data_ptr(), M, N, K, S, rope_cols, cos.data_ptr(),
                                                  sin.data_ptr(), _lib.stream_ptr(x)), "gemm_qkv_rope")
     _lib.count_launch()

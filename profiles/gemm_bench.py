@@ -16,6 +16,8 @@ def timeit(fn, n=20):
 
 def rel(a, b): return ((a.float() - b.float()).norm() / b.float().norm()).item()
 
+T.TWO_CTA = os.environ.get("ODB_TC_GEMM_2CTA", "1") != "0"
+print("two_cta =", T.TWO_CTA)
 print("== plain TN GEMM")
 for (M, N, Kd) in [(300, 520, 200), (128, 256, 64), (4096, 1024, 1024), (32768, 1024, 1024), (32768, 3072, 1024), (32768, 5376, 1024),
                    (32768, 1024, 2688), (2048, 32000, 1024), (16384, 2560, 2048), (16384, 2048, 5632)]:
