@@ -34,17 +34,29 @@ constexpr int A_BYTES = BM * BK * 2;       // 16 KB
 constexpr int B_BYTES = (BN / 2) * BK * 2; // 16 KB: this CTA's half of the 256-row B tile
 constexpr int EPI_CHUNK = 64;              // output columns per epilogue store (128 B of bf16)
 constexpr int EPI_BYTES = BM * EPI_CHUNK * 2;  // 16 KB
-constexpr int THREADS = 192;
-constexpr int EPI_THREADS = 128;
+constexpr int THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue group 0, warps 6-9 epilogue group 1
+constexpr int EPI_THREADS = 128;      // per group
+constexpr int EPI_GROUPS = 2;
+constexpr int GROUP_M = 16;           // rasterisation: 16 m-blocks x all n-blocks per super-block (L2 reuse of A and B)
 constexpr uint32_t TMEM_COLS = 512;
 
 enum Epi { kStore = 0, kSwiGLU = 1, kRoPE = 2 };
 
-template <int EPI> struct Cfg { static constexpr int STAGES = 6, NBUF = 2; };
-template <> struct Cfg<kSwiGLU> { static constexpr int STAGES = 5, NBUF = 3; };
+template <int EPI> struct Cfg { static constexpr int STAGES = 5, NBUF = 4; };     // NBUF: staging tiles (2 per epilogue group)
+template <> struct Cfg<kSwiGLU> { static constexpr int STAGES = 4, NBUF = 6; };   // 3 per epilogue group
 
 template <int EPI>
 constexpr int smem_bytes() { return Cfg<EPI>::STAGES * (A_BYTES + B_BYTES) + Cfg<EPI>::NBUF * EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/; }
+
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& m_blk, int& n_blk) {
+  const int group_size = GROUP_M * num_n;
+  const int group_id = tile / group_size;
+  const int first_m = group_id * GROUP_M;
+  const int gsz = (num_m - first_m) < GROUP_M ? (num_m - first_m) : GROUP_M;
+  const int r = tile - group_id * group_size;
+  m_blk = first_m + r % gsz;
+  n_blk = r / gsz;
+}
 
 struct Params {
   int M, N, K;
@@ -95,7 +107,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     tma_prefetch_desc(&tmap_b);
     tma_prefetch_desc(&tmap_c);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }   // 4 warps x 2 CTAs
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 16); }   // 8 epilogue warps x 2 CTAs
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_2cta(tmem_slot, TMEM_COLS);
@@ -110,8 +122,9 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m_idx = (tile % p.num_m) * (2 * BM) + (int)cta_rank * BM;
-        const int n_blk = tile / p.num_m;
+        int m_blk, n_blk;
+        tile_coords(tile, p.num_m, p.num_n, m_blk, n_blk);
+        const int m_idx = m_blk * (2 * BM) + (int)cta_rank * BM;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait_cluster(&empty_bar[stage], phase ^ 1);
           const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);   // the pair's "full" barrier lives in CTA 0
@@ -156,18 +169,22 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       }
     }
   } else if (warp >= 2) {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2..9, two groups of 4)
     const int q = warp & 3;                     // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;              // row inside the 128-row tile
-    const int epi_tid = threadIdx.x - 64;       // 0..127
+    const int eg = (warp - 2) >> 2;             // epilogue group: handles the 64-column chunks c with c % 2 == eg
+    const int epi_tid = threadIdx.x - 64 - eg * EPI_THREADS;       // 0..127 inside the group
     const bool store_thread = (epi_tid == 0);
+    const int bar_a = 1 + 2 * eg, bar_b = 2 + 2 * eg;               // named barriers private to the group
+    uint8_t* my_epi = smem_epi + eg * (NBUF / EPI_GROUPS) * EPI_BYTES;
     int it = 0;
     int buf_i = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m_idx = (tile % p.num_m) * (2 * BM) + (int)cta_rank * BM;
-      const int n_blk = tile / p.num_m;
+      int m_blk, n_blk;
+      tile_coords(tile, p.num_m, p.num_n, m_blk, n_blk);
+      const int m_idx = m_blk * (2 * BM) + (int)cta_rank * BM;
       const uint32_t leader_tmem_empty = mapa_shared(smem_u32(&tmem_empty[acc]), 0);
       mbar_wait_cluster(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
@@ -175,8 +192,8 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 
       if constexpr (EPI == kSwiGLU) {
         const int n0 = n_blk * (BN / 2);
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
+        {
+          const int c = eg;
           float g[64], u[64];
           {
             uint32_t r0[32], r1[32];
@@ -191,16 +208,16 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 #pragma unroll
             for (int j = 0; j < 32; ++j) { u[j] = __uint_as_float(r0[j]); u[32 + j] = __uint_as_float(r1[j]); }
           }
-          if (c == 1) {   // accumulator fully drained into registers: hand it back to the MMA warp
+          {   // this warp's share of the accumulator is in registers: hand it back to the MMA warp
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(leader_tmem_empty);
           }
           if (store_thread) tma_store_wait_read<0>();
-          named_bar_sync(1, EPI_THREADS);
-          uint8_t* bg = smem_epi;
-          uint8_t* bu = smem_epi + EPI_BYTES;
-          uint8_t* ba = smem_epi + 2 * EPI_BYTES;
+          named_bar_sync(bar_a, EPI_THREADS);
+          uint8_t* bg = my_epi;
+          uint8_t* bu = my_epi + EPI_BYTES;
+          uint8_t* ba = my_epi + 2 * EPI_BYTES;
           stage_row_bf16(bg, row, g);
           stage_row_bf16(bu, row, u);
 #pragma unroll
@@ -211,7 +228,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           }
           stage_row_bf16(ba, row, g);
           fence_proxy_async_smem();
-          named_bar_sync(2, EPI_THREADS);
+          named_bar_sync(bar_b, EPI_THREADS);
           if (store_thread) {
             tma_store_2d(&tmap_c, bg, n0 + c * 64, m_idx);
             tma_store_2d(&tmap_c, bu, p.I + n0 + c * 64, m_idx);
@@ -237,7 +254,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           }
         }
 #pragma unroll 1
-        for (int c = 0; c < BN / EPI_CHUNK; ++c) {
+        for (int c = eg; c < BN / EPI_CHUNK; c += EPI_GROUPS) {
           float v[64];
           {
             uint32_t r0[32], r1[32];
@@ -247,7 +264,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 #pragma unroll
             for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
           }
-          if (c == BN / EPI_CHUNK - 1) {
+          if (c >= BN / EPI_CHUNK - EPI_GROUPS) {      // this warp's last chunk of the tile
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(leader_tmem_empty);
@@ -262,12 +279,12 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
               }
             }
           }
-          uint8_t* buf = smem_epi + (buf_i & 1) * EPI_BYTES;
+          uint8_t* buf = my_epi + (buf_i & 1) * EPI_BYTES;
           if (store_thread) tma_store_wait_read<1>();      // the store that last read this buffer has drained
-          named_bar_sync(1, EPI_THREADS);
+          named_bar_sync(bar_a, EPI_THREADS);
           stage_row_bf16(buf, row, v);
           fence_proxy_async_smem();
-          named_bar_sync(2, EPI_THREADS);
+          named_bar_sync(bar_b, EPI_THREADS);
           if (store_thread) {
             tma_store_2d(&tmap_c, buf, n_blk * BN + c * 64, m_idx);
             tma_store_commit();

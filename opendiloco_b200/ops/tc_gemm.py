@@ -27,9 +27,12 @@ ENABLED = os.environ.get("ODB_TC_GEMM", "1") != "0"
 TWO_CTA = os.environ.get("ODB_TC_GEMM_2CTA", "1") != "0"     # CTA-pair (cta_group::2, 256x256 tiles) kernels
 
 
-def _fn(name: str):
+def _fn(name: str, M: int = 1 << 30, N: int = 1 << 30):
+    """CTA-pair kernel (256x256 tiles) for problems with at least one full wave of pair-tiles, else 128x256 tiles."""
     lib = _lib.cuda_lib()
-    return getattr(lib, name.replace("odb_gemm_", "odb_gemm2_") if TWO_CTA else name)
+    pair_tiles = ((M + 255) // 256) * ((N + 255) // 256)
+    two = TWO_CTA and pair_tiles >= 74
+    return getattr(lib, name.replace("odb_gemm_", "odb_gemm2_") if two else name)
 
 
 def usable(*tensors: torch.Tensor) -> bool:
@@ -42,7 +45,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor | None = None) ->
     N = w.shape[0]
     if out is None:
         out = torch.empty(M, N, dtype=x.dtype, device=x.device)
-    _lib.check(_fn("odb_gemm_bf16_tn")(x.data_ptr(), w.data_ptr(), out.data_ptr(), M, N, K, x.stride(0), w.stride(0),
+    _lib.check(_fn("odb_gemm_bf16_tn", M, N)(x.data_ptr(), w.data_ptr(), out.data_ptr(), M, N, K, x.stride(0), w.stride(0),
                                                 out.stride(0), _lib.stream_ptr(x)), "gemm_bf16_tn")
     _lib.count_launch()
     return out
@@ -52,7 +55,7 @@ def linear_swiglu(x: torch.Tensor, w_gu: torch.Tensor, gu: torch.Tensor, act: to
     M, K = x.shape
     I = w_gu.shape[0] // 2
     assert x.is_contiguous() and w_gu.is_contiguous() and gu.is_contiguous() and act.is_contiguous()
-    _lib.check(_fn("odb_gemm_swiglu")(x.data_ptr(), w_gu.data_ptr(), gu.data_ptr(), act.data_ptr(), M, I, K,
+    _lib.check(_fn("odb_gemm_swiglu", M, I // 128 * 256)(x.data_ptr(), w_gu.data_ptr(), gu.data_ptr(), act.data_ptr(), M, I, K,
                                                _lib.stream_ptr(x)), "gemm_swiglu")
     _lib.count_launch()
 
@@ -62,6 +65,6 @@ def linear_qkv_rope(x: torch.Tensor, w: torch.Tensor, qkv: torch.Tensor, cos: to
     M, K = x.shape
     N = w.shape[0]
     assert x.is_contiguous() and w.is_contiguous() and qkv.is_contiguous() and cos.shape[1] == 32
-    _lib.check(_fn("odb_gemm_qkv_rope")(x.data_ptr(), w.data_ptr(), qkv.data_ptr(), M, N, K, S, rope_cols, cos.data_ptr(),
+    _lib.check(_fn("odb_gemm_qkv_rope", M, N)(x.data_ptr(), w.data_ptr(), qkv.data_ptr(), M, N, K, S, rope_cols, cos.data_ptr(),
                                                  sin.data_ptr(), _lib.stream_ptr(x)), "gemm_qkv_rope")
     _lib.count_launch()
