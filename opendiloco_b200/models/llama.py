@@ -140,8 +140,11 @@ class LlamaEngine:
             # --- MLP block:  xm = xa + proj ; xn2 = norm(xm)
             K.rmsnorm_fwd(ws.xa[l], ar.w(p + "post_attention_layernorm.weight"), cfg.rms_norm_eps, delta=ws.proj,
                           out=ws.xn2[l], rstd=ws.rstd2[l], x_out=ws.xm[l])
-            G.mm_nt(ws.xn2[l], ar.gu_w(l), out=ws.gu[l])
-            K.swiglu_fwd(ws.gu[l], out=ws.act[l])
+            if cfg.intermediate_size % 64 == 0 and TC.usable(ws.xn2[l], ar.gu_w(l)):
+                TC.linear_swiglu(ws.xn2[l], ar.gu_w(l), ws.gu[l], ws.act[l])     # SwiGLU is the GEMM epilogue
+            else:
+                G.mm_nt(ws.xn2[l], ar.gu_w(l), out=ws.gu[l])
+                K.swiglu_fwd(ws.gu[l], out=ws.act[l])
             G.mm_nt(ws.act[l], ar.w(p + "mlp.down_proj.weight"), out=ws.proj)
             delta = ws.proj
         K.rmsnorm_fwd(ws.xm[L - 1], ar.w("model.norm.weight"), cfg.rms_norm_eps, delta=delta, out=ws.xnf, rstd=ws.rstdf,
@@ -171,6 +174,7 @@ class LlamaEngine:
         ws.gscale.mul_(float(loss_scale))
         ws.loss_sum.zero_()
         w_lm = ar.w("lm_head.weight")
+        w_lm_t = ar.wT("lm_head.weight", V, cfg.hidden_size) if with_grad else None
         hooked = self.module_hooks.get("lm_head")
         want_norm = self.collect_act_norms or (hooked is not None and bool(hooked._forward_hooks))
         if want_norm:
@@ -191,7 +195,7 @@ class LlamaEngine:
             G.mm_nt(ws.xnf[c0:c1], w_lm, out=logits)
             if with_grad:
                 K.ce_fwd_bwd_(logits, ws.labels[c0:c1], ws.gscale, ws.loss_sum, ws.sumsq if want_norm else None)
-                G.mm_nn(logits, w_lm, out=ws.dxnf[c0:c1])
+                G.mm_nn(logits, w_lm, out=ws.dxnf[c0:c1], b_t=w_lm_t)
                 G.mm_tn_acc(logits, ws.xnf[c0:c1], g_lm)
             else:
                 if want_norm:
@@ -215,27 +219,28 @@ class LlamaEngine:
         cfg, ar = self.cfg, self.arena
         B, S, L = ws.B, ws.S, cfg.num_hidden_layers
         Hq, Hkv, D = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
+        h, i = cfg.hidden_size, cfg.intermediate_size
         K.rmsnorm_bwd(ws.dxnf, ws.xf, ar.w("model.norm.weight"), ws.rstdf, None, ws.dx, ar.g("model.norm.weight"))
         for l in reversed(range(L)):
             p = f"model.layers.{l}."
             # ---- MLP block (ws.dx is the gradient of x_out = xm + down(act))
             G.mm_tn_acc(ws.dx, ws.act[l], ar.g(p + "mlp.down_proj.weight"))
-            G.mm_nn(ws.dx, ar.w(p + "mlp.down_proj.weight"), out=ws.dact)
+            G.mm_nn(ws.dx, ar.w(p + "mlp.down_proj.weight"), out=ws.dact, b_t=ar.wT(p + "mlp.down_proj.weight", h, i))
             K.swiglu_bwd(ws.dact, ws.gu[l], ws.gu[l])                      # in place: gu <- d(gu)
             G.mm_tn_acc(ws.gu[l], ws.xn2[l], ar.gu_g(l))
-            G.mm_nn(ws.gu[l], ar.gu_w(l), out=ws.dn)
+            G.mm_nn(ws.gu[l], ar.gu_w(l), out=ws.dn, b_t=ar.wT(p + "mlp.gate_proj.weight", 2 * i, h))
             K.rmsnorm_bwd(ws.dn, ws.xm[l], ar.w(p + "post_attention_layernorm.weight"), ws.rstd2[l], ws.dx, ws.dx,
                           ar.g(p + "post_attention_layernorm.weight"))
             # ---- attention block (ws.dx is now the gradient of xm = xa + o(att))
             G.mm_tn_acc(ws.dx, ws.att[l], ar.g(p + "self_attn.o_proj.weight"))
-            G.mm_nn(ws.dx, ar.w(p + "self_attn.o_proj.weight"), out=ws.datt)
+            G.mm_nn(ws.dx, ar.w(p + "self_attn.o_proj.weight"), out=ws.datt, b_t=ar.wT(p + "self_attn.o_proj.weight", h, cfg.q_dim))
             if attention_mask is None:
                 A.attention_bwd(ws.datt, ws.qkv[l], ws.att[l], ws.aux[l], ws.dqkv, B, S, Hq, Hkv, D)
             else:
                 _masked_attention_bwd(ws.datt, ws.aux[l], ws.dqkv, B, S, Hq, Hkv, D)
             K.rope_(ws.dqkv, ws.cos, ws.sin, S, Hq + Hkv, D, backward=True)
             G.mm_tn_acc(ws.dqkv, ws.xn1[l], ar.qkv_g(l))
-            G.mm_nn(ws.dqkv, ar.qkv_w(l), out=ws.dn)
+            G.mm_nn(ws.dqkv, ar.qkv_w(l), out=ws.dn, b_t=ar.wT(p + "self_attn.q_proj.weight", cfg.qkv_dim, h))
             K.rmsnorm_bwd(ws.dn, ws.xa[l], ar.w(p + "input_layernorm.weight"), ws.rstd1[l], ws.dx, ws.dx,
                           ar.g(p + "input_layernorm.weight"))
             ws.att[l] = None

@@ -14,16 +14,25 @@ from __future__ import annotations
 
 import torch
 
+from . import tc_gemm as TC
+
 _ADDMM_DTYPE_OK: bool | None = None
 
 
 def mm_nt(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """a[M,K] @ b[N,K]^T : our tcgen05 kernel for CUDA bf16 operands, cuBLAS/ATen otherwise (fp32, fp16, CPU)."""
+    if TC.usable(a, b) and (out is None or TC.usable(out)):
+        return TC.linear(a, b, out)
     if out is None:
         return torch.mm(a, b.t())
     return torch.mm(a, b.t(), out=out)
 
 
-def mm_nn(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+def mm_nn(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, b_t: torch.Tensor | None = None) -> torch.Tensor:
+    """a[M,N] @ b[N,K] (dgrad).  With ``b_t`` = b^T stored row-major ([K,N]) the product is a K-major "TN" GEMM and runs
+    on the tcgen05 kernel; the arena keeps such transposed bf16 copies of the weights."""
+    if b_t is not None and TC.usable(a, b_t) and (out is None or TC.usable(out)):
+        return TC.linear(a, b_t, out)
     if out is None:
         return torch.mm(a, b)
     return torch.mm(a, b, out=out)

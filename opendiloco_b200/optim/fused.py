@@ -34,6 +34,12 @@ class FlatView:
         self.params, self.flat, self.grad, self.offsets, self.shadow = params, flat, grad, offsets, shadow
         self.lo, self.hi = 0, flat.numel()
         self.shard_group = None
+        self.arena = getattr(params[0], "_odb_arena", None) if params else None
+
+    def mark_dirty(self) -> None:
+        """The compute weights changed: derived copies (transposed bf16 weights) must be rebuilt before their next use."""
+        if self.arena is not None:
+            self.arena.shadow_dirty = True
 
     @property
     def numel(self) -> int:
@@ -60,6 +66,7 @@ class FlatView:
     def gather_compute_weights(self) -> None:
         """After a sharded update: every rank publishes its slice of the compute weights (bf16 shadow, or fp32 master
         when computing in fp32) to the worker's other GPUs."""
+        self.mark_dirty()
         if not self.sharded:
             return
         buf = self.shadow if self.shadow is not None else self.flat

@@ -402,7 +402,7 @@ class DiLoCoStateAverager:
             if g is not None and same_dev and (g.get("momentum", 0) != 0):
                 K.nesterov_outer(self.theta_outer, self.momentum_buffer, None if fused_solo else self.delta,
                                  self.theta_local, self.shadow_local, g["lr"], g["momentum"], bool(g.get("nesterov", False)))
-                self.fv.gather_compute_weights()
+                self.fv.gather_compute_weights()      # also marks derived weight copies dirty
             else:
                 if fused_solo:
                     K.pseudo_grad(self.theta_outer, self.theta_local.to(self.theta_outer.device), self.delta)

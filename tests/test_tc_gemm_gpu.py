@@ -1,0 +1,70 @@
+"""tcgen05 GEMM family (1-CTA and CTA-pair kernels, fused SwiGLU / RoPE epilogues) against fp32 PyTorch references."""
+import pytest
+import torch
+
+from opendiloco_b200.ops import kernels as K
+from opendiloco_b200.ops import tc_gemm as T
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
+
+
+@pytest.fixture(params=[False, True], ids=["1cta", "2cta"])
+def two_cta(request, monkeypatch):
+    monkeypatch.setattr(T, "TWO_CTA", request.param)
+    return request.param
+
+
+@pytest.mark.parametrize("M,N,Kd", [(128, 256, 64), (300, 520, 200), (1000, 136, 72), (4096, 1024, 1024), (20000, 768, 2688)])
+def test_linear_matches_fp32(two_cta, M, N, Kd):
+    torch.manual_seed(0)
+    x = torch.randn(M, Kd, device="cuda").to(BF)
+    w = (torch.randn(N, Kd, device="cuda") * 0.1).to(BF)
+    out = T.linear(x, w)
+    ref = x.float() @ w.float().t()
+    assert rel(out, ref) < 4e-3
+    assert torch.equal(out, torch.mm(x, w.t()))        # same fp32 accumulation + single bf16 rounding as cuBLAS
+
+
+def test_linear_strided_views(two_cta):
+    torch.manual_seed(1)
+    big = torch.randn(600, 1024, device="cuda").to(BF)
+    x = big[:, 256:768]                                  # row stride 1024, 512 columns
+    w = (torch.randn(320, 512, device="cuda") * 0.1).to(BF)
+    outbuf = torch.zeros(600, 640, device="cuda", dtype=BF)
+    T.linear(x, w, outbuf[:, 320:])
+    assert rel(outbuf[:, 320:], x.float() @ w.float().t()) < 4e-3
+    assert torch.count_nonzero(outbuf[:, :320]) == 0     # TMA store clipped to the view
+
+
+@pytest.mark.parametrize("M,I,Kd", [(256, 128, 64), (777, 384, 192), (20000, 2688, 1024)])
+def test_swiglu_epilogue(two_cta, M, I, Kd):
+    torch.manual_seed(2)
+    x = torch.randn(M, Kd, device="cuda").to(BF)
+    w = (torch.randn(2 * I, Kd, device="cuda") * 0.1).to(BF)
+    gu, act = torch.empty(M, 2 * I, device="cuda", dtype=BF), torch.empty(M, I, device="cuda", dtype=BF)
+    T.linear_swiglu(x, w, gu, act)
+    gu_ref = torch.mm(x, w.t())
+    assert torch.equal(gu, gu_ref)
+    g, u = gu_ref[:, :I].float(), gu_ref[:, I:].float()
+    assert rel(act, torch.nn.functional.silu(g) * u) < 4e-3
+
+
+@pytest.mark.parametrize("B,S,Hq,Hkv,Kd", [(2, 128, 4, 4, 256), (3, 256, 8, 2, 512), (16, 1024, 16, 16, 1024)])
+def test_qkv_rope_epilogue(two_cta, B, S, Hq, Hkv, Kd):
+    torch.manual_seed(3)
+    M, N = B * S, (Hq + 2 * Hkv) * 64
+    x = torch.randn(M, Kd, device="cuda").to(BF)
+    w = (torch.randn(N, Kd, device="cuda") * 0.1).to(BF)
+    cos, sin = K.rope_tables(S, 64, 10000.0, "cuda")
+    ref = torch.mm(x, w.t())
+    v_ref = ref[:, (Hq + Hkv) * 64:].clone()
+    K.rope_(ref, cos, sin, S, Hq + Hkv, 64)
+    out = torch.empty_like(ref)
+    T.linear_qkv_rope(x, w, out, cos, sin, S, (Hq + Hkv) * 64)
+    assert rel(out, ref) < 1e-3
+    assert torch.equal(out[:, (Hq + Hkv) * 64:], v_ref)   # v is not rotated
