@@ -126,7 +126,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         tile_coords(tile, p.num_m, p.num_n, m_blk, n_blk);
         const int m_idx = m_blk * (2 * BM) + (int)cta_rank * BM;
         for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait_cluster(&empty_bar[stage], phase ^ 1);
+          mbar_wait(&empty_bar[stage], phase ^ 1);
           const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);   // the pair's "full" barrier lives in CTA 0
           if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_BYTES + B_BYTES));
           tma_load_2d_2cta(smem_a + stage * A_BYTES, &tmap_a, leader_full, kb * BK, m_idx);
@@ -147,11 +147,11 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1);
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + acc * BN;
       for (int kb = 0; kb < num_k; ++kb) {
-        mbar_wait_cluster(&full_bar[stage], phase);
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after_sync();
         if (elect_one()) {
           const uint64_t adesc = make_smem_desc_sw128(smem_u32(smem_a + stage * A_BYTES), 16, 1024);
@@ -186,7 +186,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       tile_coords(tile, p.num_m, p.num_n, m_blk, n_blk);
       const int m_idx = m_blk * (2 * BM) + (int)cta_rank * BM;
       const uint32_t leader_tmem_empty = mapa_shared(smem_u32(&tmem_empty[acc]), 0);
-      mbar_wait_cluster(&tmem_full[acc], acc_phase);
+      mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
 
@@ -224,7 +224,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           for (int j = 0; j < 64; ++j) {
             const float gj = bf16_round(g[j]);     // the activation is computed from the bf16 values the backward will see
             const float uj = bf16_round(u[j]);
-            g[j] = gj / (1.f + __expf(-gj)) * uj;
+            g[j] = __fdividef(gj, 1.f + __expf(-gj)) * uj;
           }
           stage_row_bf16(ba, row, g);
           fence_proxy_async_smem();

@@ -84,7 +84,7 @@ class _Workspace:
 
 
 class LlamaEngine:
-    def __init__(self, cfg: LlamaConfig, arena: ParamArena, lce_chunk: int = 2048):
+    def __init__(self, cfg: LlamaConfig, arena: ParamArena, lce_chunk: int = 8192):
         self.cfg, self.arena = cfg, arena
         self.lce_chunk = lce_chunk
         self._ws: dict[tuple, _Workspace] = {}
@@ -346,7 +346,7 @@ class LlamaForCausalLM(nn.Module):
     """Drop-in for the HF class the reference trains (train_fsdp.py:171-174, train_diloco_torch.py:183)."""
 
     def __init__(self, config: LlamaConfig, device=None, precision: str = "bf16-mixed", seed: int | None = None,
-                 init: bool = True, lce_chunk: int = 2048):
+                 init: bool = True, lce_chunk: int = 8192):
         super().__init__()
         self.config = config
         self.precision = precision
