@@ -114,7 +114,7 @@ def run_ours(a) -> dict:
     from opendiloco_b200.models.llama import LlamaForCausalLM
     from opendiloco_b200.parallel import comm
     from opendiloco_b200.trainer import DiLoCoTrainer, TrainerConfig
-    from opendiloco_b200.utils.data import SyntheticTokenLoader
+    from opendiloco_b200.utils.data import NativeTokenLoader, SyntheticTokenLoader
 
     world = int(os.environ.get("WORLD_SIZE", 1))
     rank = int(os.environ.get("RANK", 0))
@@ -138,7 +138,10 @@ def run_ours(a) -> dict:
                                             total_steps=88_000, compression=compression,
                                             fused_collective=False if a.no_fused_collective else None), topo)
     tr.broadcast_initial_weights()
-    loader = SyntheticTokenLoader(a.micro_batch, a.seq, vocab_size=cfg.vocab_size, seed=1234, rank=rank, with_mask=False)
+    try:      # C++ prefetcher filling pinned buffers (csrc/host/tokengen.cc)
+        loader = NativeTokenLoader(a.micro_batch, a.seq, vocab_size=cfg.vocab_size, seed=1234, rank=rank)
+    except RuntimeError:
+        loader = SyntheticTokenLoader(a.micro_batch, a.seq, vocab_size=cfg.vocab_size, seed=1234, rank=rank, with_mask=False)
     tokens_per_step = a.batch * a.seq * world
 
     def sync():
@@ -203,7 +206,7 @@ def run_ours(a) -> dict:
     if not a.no_e2e:
         h2d = a.micro_batch * a.seq * 8 * accum          # int64 input ids (labels alias the ids on the host)
         d2h = 4
-        for _ in range(2):
+        for _ in range(a.warmup):
             float(tr.train_step(loader).item())
         sync()
         t0 = time.perf_counter()

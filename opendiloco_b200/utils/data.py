@@ -92,6 +92,89 @@ class SyntheticTokenLoader:
         self.batches_yielded = int(sd["batches_yielded"])
 
 
+class NativeTokenLoader:
+    """SyntheticTokenLoader backed by the C++ prefetcher (``csrc/host/tokengen.cc``): a background thread keeps a ring
+    of PINNED [B, S] int64 buffers filled, so ``next()`` is a pointer hand-off and the H2D copy is the only per-batch
+    host work.  The stream is a pure function of (seed, rank, batch index) => ``state_dict`` is one integer."""
+
+    def __init__(self, batch_size: int, seq_len: int, vocab_size: int = TEST_VOCAB_SIZE, seed: int = 0, rank: int = 0,
+                 nbuf: int = 8, pin_memory: bool | None = None):
+        import ctypes
+
+        from .. import _lib
+
+        lib = _lib.host_lib()
+        if lib is None or not hasattr(lib, "odb_tg_create"):
+            raise RuntimeError("libodbhost.so is not built (python -m opendiloco_b200.build)")
+        self._ct, self._lib = ctypes, lib
+        lib.odb_tg_create.restype = ctypes.c_void_p
+        lib.odb_tg_create.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
+                                      ctypes.POINTER(ctypes.c_void_p), ctypes.c_int64]
+        lib.odb_tg_next.argtypes = [ctypes.c_void_p]
+        lib.odb_tg_release.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        lib.odb_tg_position.argtypes = [ctypes.c_void_p]
+        lib.odb_tg_position.restype = ctypes.c_int64
+        lib.odb_tg_destroy.argtypes = [ctypes.c_void_p]
+        pin = torch.cuda.is_available() if pin_memory is None else pin_memory
+        self.batch_size, self.seq_len, self.vocab_size = batch_size, seq_len, vocab_size
+        self.seed = (seed * 1_000_003 + rank) & 0xFFFFFFFFFFFFFFFF
+        self.bufs = [torch.empty(batch_size, seq_len, dtype=torch.int64, pin_memory=pin) for _ in range(nbuf)]
+        self._h = None
+        self._held: int | None = None
+        self._inflight: list = []          # (slot, cuda event) pairs whose H2D copy may still be running
+        self._start(0)
+
+    def _start(self, batch_index: int) -> None:
+        ct = self._ct
+        arr = (ct.c_void_p * len(self.bufs))(*[b.data_ptr() for b in self.bufs])
+        self._h = self._lib.odb_tg_create(self.seed, 3, self.vocab_size, self.batch_size * self.seq_len, len(self.bufs), arr,
+                                          batch_index)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self) -> dict[str, torch.Tensor]:
+        # The consumer enqueues its (async) H2D copy of a batch before asking for the next one, so an event recorded
+        # NOW on the current stream covers the copy of the previously handed-out slot.  A slot goes back to the
+        # prefetch thread only after that event completed: the CPU may run up to nbuf-2 micro-batches ahead of the GPU.
+        if self._held is not None:
+            ev = None
+            if torch.cuda.is_available() and self.bufs[0].is_pinned():
+                ev = torch.cuda.Event()
+                ev.record()
+            self._inflight.append((self._held, ev))
+        while len(self._inflight) > len(self.bufs) - 2:
+            slot, ev = self._inflight.pop(0)
+            if ev is not None:
+                ev.synchronize()
+            self._lib.odb_tg_release(self._h, slot)
+        slot = self._lib.odb_tg_next(self._h)
+        self._held = slot
+        ids = self.bufs[slot]
+        return {"input_ids": ids, "labels": ids}
+
+    def state_dict(self) -> dict:
+        pos = self._lib.odb_tg_position(self._h)
+        return {"batches_yielded": int(pos)}
+
+    def load_state_dict(self, sd: dict) -> None:
+        self.close()
+        self._held = None
+        self._inflight = []
+        self._start(int(sd["batches_yielded"]))
+
+    def close(self) -> None:
+        if self._h is not None:
+            self._lib.odb_tg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def data_rank(world_rank: int | None, galaxy_size: int | None, world_size: int, rank: int, local_rank: int) -> tuple[int, int]:
     """(shard index, number of shards) with the reference's worker-major rule (train_fsdp.py:151-156)."""
     if galaxy_size is not None and world_rank is not None:

@@ -30,7 +30,48 @@ def read_header(path: str) -> tuple[dict, int]:
     return header, 8 + n
 
 
+def _load_native(path: str) -> dict[str, torch.Tensor] | None:
+    """Header parsing + bounds validation in C++ (csrc/host/safetensors.cc); tensors are copied out of the mmap."""
+    import ctypes
+
+    from .. import _lib
+
+    lib = _lib.host_lib()
+    if lib is None or not hasattr(lib, "odb_st_open"):
+        return None
+    lib.odb_st_open.restype = ctypes.c_void_p
+    lib.odb_st_open.argtypes = [ctypes.c_char_p]
+    for fn, res in (("odb_st_error", ctypes.c_char_p), ("odb_st_name", ctypes.c_char_p), ("odb_st_dtype", ctypes.c_char_p),
+                    ("odb_st_count", ctypes.c_int), ("odb_st_ndim", ctypes.c_int), ("odb_st_dim", ctypes.c_int64),
+                    ("odb_st_nbytes", ctypes.c_uint64), ("odb_st_data", ctypes.c_void_p), ("odb_st_close", None)):
+        getattr(lib, fn).restype = res
+    lib.odb_st_error.argtypes = lib.odb_st_count.argtypes = lib.odb_st_close.argtypes = [ctypes.c_void_p]
+    for fn in ("odb_st_name", "odb_st_dtype", "odb_st_ndim", "odb_st_nbytes", "odb_st_data"):
+        getattr(lib, fn).argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.odb_st_dim.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    h = lib.odb_st_open(path.encode())
+    try:
+        err = lib.odb_st_error(h)
+        if err:
+            raise ValueError(f"{path}: {err.decode()}")
+        out = {}
+        for i in range(lib.odb_st_count(h)):
+            dt = _DTYPES[lib.odb_st_dtype(h, i).decode()]
+            shape = [lib.odb_st_dim(h, i, d) for d in range(lib.odb_st_ndim(h, i))]
+            n = lib.odb_st_nbytes(h, i)
+            raw = torch.empty(n, dtype=torch.uint8)
+            if n:
+                ctypes.memmove(raw.data_ptr(), lib.odb_st_data(h, i), n)
+            out[lib.odb_st_name(h, i).decode()] = raw.view(dt).reshape(shape)
+        return out
+    finally:
+        lib.odb_st_close(h)
+
+
 def load_safetensors(path: str) -> dict[str, torch.Tensor]:
+    native = _load_native(path)
+    if native is not None:
+        return native
     header, base = read_header(path)
     out: dict[str, torch.Tensor] = {}
     with open(path, "rb") as f:
