@@ -65,6 +65,8 @@ struct Params {
   int S, rope_cols;          // kRoPE: sequence length, number of leading columns that get rotated
   const float* cos_t;        // [S, 32] fp32 (head_dim 64)
   const float* sin_t;
+  int ks1, ks2;              // A operand split along K into up to three tensors: k-blocks [0,ks1) from A, [ks1,ks2) from A1,
+                             // [ks2,..) from A2 (0/0 = single tensor).  Lets dq|dk|dv feed one dgrad GEMM without packing.
 };
 
 // write one 64-column chunk of this thread's row into the swizzled staging tile (row r, 8 x 16-byte chunks)
@@ -82,7 +84,8 @@ __device__ __forceinline__ void stage_row_bf16(uint8_t* buf, int row, const floa
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_aux, Params p) {
+                    const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_aux,
+                    const __grid_constant__ CUtensorMap tmap_a1, const __grid_constant__ CUtensorMap tmap_a2, Params p) {
   constexpr int STAGES = Cfg<EPI>::STAGES;
   constexpr int NBUF = Cfg<EPI>::NBUF;
   extern __shared__ uint8_t smem_raw[];
@@ -129,7 +132,9 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           mbar_wait(&empty_bar[stage], phase ^ 1);
           const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);   // the pair's "full" barrier lives in CTA 0
           if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_BYTES + B_BYTES));
-          tma_load_2d_2cta(smem_a + stage * A_BYTES, &tmap_a, leader_full, kb * BK, m_idx);
+          if (p.ks1 == 0 || kb < p.ks1) tma_load_2d_2cta(smem_a + stage * A_BYTES, &tmap_a, leader_full, kb * BK, m_idx);
+          else if (kb < p.ks2) tma_load_2d_2cta(smem_a + stage * A_BYTES, &tmap_a1, leader_full, (kb - p.ks1) * BK, m_idx);
+          else tma_load_2d_2cta(smem_a + stage * A_BYTES, &tmap_a2, leader_full, (kb - p.ks2) * BK, m_idx);
           int b_row;
           if constexpr (EPI == kSwiGLU) b_row = (cta_rank == 0) ? n_blk * (BN / 2) : p.I + n_blk * (BN / 2);   // gate half | up half
           else b_row = n_blk * BN + (int)cta_rank * (BN / 2);
@@ -301,14 +306,25 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   if (warp == 1) tmem_dealloc_2cta(tmem_base, TMEM_COLS);
 }
 
+struct ASplit {
+  const void* A1 = nullptr; const void* A2 = nullptr;
+  long long lda1 = 0, lda2 = 0;
+  int K0 = 0, K1 = 0, K2 = 0;      // K extents of the three A tensors (multiples of 64); K0 == 0 => no split
+};
+
 template <int EPI>
 static int launch(const void* A, const void* B, void* C, void* aux, int M, int N, int K, long long lda, long long ldb,
                   long long ldc, long long ldaux, int I, int S, int rope_cols, const float* cos_t, const float* sin_t,
-                  cudaStream_t st) {
-  CUtensorMap ta, tb, tc, tx;
+                  cudaStream_t st, const ASplit& sp = ASplit()) {
+  CUtensorMap ta, tb, tc, tx, ta1, ta2;
   int rc;
   const int n_out = (EPI == kSwiGLU) ? 2 * I : N;
-  if ((rc = make_tmap_2d(&ta, A, M, K, lda * 2, BM, BK, 2))) return rc;
+  if ((rc = make_tmap_2d(&ta, A, M, sp.K0 ? sp.K0 : K, lda * 2, BM, BK, 2))) return rc;
+  ta1 = ta; ta2 = ta;
+  if (sp.K0) {
+    if ((rc = make_tmap_2d(&ta1, sp.A1, M, sp.K1, sp.lda1 * 2, BM, BK, 2))) return rc;
+    if ((rc = make_tmap_2d(&ta2, sp.A2, M, sp.K2, sp.lda2 * 2, BM, BK, 2))) return rc;
+  }
   if ((rc = make_tmap_2d(&tb, B, (EPI == kSwiGLU) ? 2 * I : N, K, ldb * 2, BN / 2, BK, 2))) return rc;
   if ((rc = make_tmap_2d(&tc, C, M, n_out, ldc * 2, BM, EPI_CHUNK, 2))) return rc;
   if (EPI == kSwiGLU) {
@@ -321,6 +337,8 @@ static int launch(const void* A, const void* B, void* C, void* aux, int M, int N
   p.num_m = ceil_div(M, 2 * BM);
   p.num_n = (EPI == kSwiGLU) ? ceil_div(I, BN / 2) : ceil_div(N, BN);
   p.I = I; p.S = S > 0 ? S : 1; p.rope_cols = rope_cols; p.cos_t = cos_t; p.sin_t = sin_t;
+  p.ks1 = sp.K0 ? sp.K0 / BK : 0;
+  p.ks2 = sp.K0 ? (sp.K0 + sp.K1) / BK : 0;
   static bool attr_set = false;
   constexpr int smem = smem_bytes<EPI>();
   if (!attr_set) {
@@ -331,7 +349,7 @@ static int launch(const void* A, const void* B, void* C, void* aux, int M, int N
   const int tiles = p.num_m * p.num_n;
   const int max_clusters = sm_count() / 2;
   const int grid = 2 * (tiles < max_clusters ? tiles : max_clusters);
-  gemm2_bf16_tn_kernel<EPI><<<grid, THREADS, smem, st>>>(ta, tb, tc, tx, p);    // cluster dims are compiled in (__cluster_dims__)
+  gemm2_bf16_tn_kernel<EPI><<<grid, THREADS, smem, st>>>(ta, tb, tc, tx, ta1, ta2, p);    // cluster dims are compiled in (__cluster_dims__)
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }
@@ -357,4 +375,14 @@ ODB_EXPORT int odb_gemm2_qkv_rope(const void* X, const void* W, void* qkv, int M
   if (K % 8 || N % 64 || rope_cols % 64) return -1;
   return gemm2::launch<gemm2::kRoPE>(X, W, qkv, nullptr, M, N, K, K, K, N, 0, 0, S, rope_cols, (const float*)cos_t,
                                    (const float*)sin_t, st);
+}
+
+// C[M,N] = [A0 | A1 | A2][M, K0+K1+K2] * B[N, K0+K1+K2]^T without materialising the concatenation (K segments % 64 == 0)
+ODB_EXPORT int odb_gemm2_bf16_tn_a3(const void* A0, const void* A1, const void* A2, long long lda0, long long lda1, long long lda2,
+                                    int K0, int K1, int K2, const void* B, void* C, int M, int N, long long ldb, long long ldc,
+                                    cudaStream_t st) {
+  if (K0 % 64 || K1 % 64 || K2 % 64 || K0 <= 0 || K1 <= 0 || K2 <= 0) return -1;
+  gemm2::ASplit sp;
+  sp.A1 = A1; sp.A2 = A2; sp.lda1 = lda1; sp.lda2 = lda2; sp.K0 = K0; sp.K1 = K1; sp.K2 = K2;
+  return gemm2::launch<gemm2::kStore>(A0, B, C, nullptr, M, N, K0 + K1 + K2, lda0, ldb, ldc, 0, 0, 0, 0, nullptr, nullptr, st, sp);
 }

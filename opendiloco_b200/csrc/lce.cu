@@ -40,7 +40,10 @@ __global__ void __launch_bounds__(256) ce_fwd_bwd_kernel(__nv_bfloat16* __restri
     }
   }
   mx = block_max(mx, sm);
+  // exp() once per element: the fp32 values feed the row sum, their bf16 roundings replace the logits in registers and
+  // become the softmax numerators of the second pass (the output is bf16 anyway).  The label logit is picked up here.
   float s = 0.f;
+  float x_label = 0.f;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const int c = threadIdx.x + k * 256;
@@ -48,10 +51,16 @@ __global__ void __launch_bounds__(256) ce_fwd_bwd_kernel(__nv_bfloat16* __restri
       float f[8];
       unpack8(raw[k], f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s += __expf(f[j] - mx);
+      for (int j = 0; j < 8; ++j) {
+        if ((long long)(c * 8 + j) == y) x_label = f[j];
+        f[j] = __expf(f[j] - mx);
+        s += f[j];
+      }
+      raw[k] = pack8(f);
     }
   }
   s = block_sum(s, sm);
+  x_label = block_sum(x_label, sm);     // exactly one thread holds a non-zero value
   if (sumsq) {
     sq = block_sum(sq, sm);
     if (threadIdx.x == 0) atomicAdd(sumsq, sq);
@@ -59,6 +68,7 @@ __global__ void __launch_bounds__(256) ce_fwd_bwd_kernel(__nv_bfloat16* __restri
   const float lse = mx + __logf(s);
   const float gscale = ignore ? 0.f : *gscale_ptr;
   const float inv_s = gscale / s;
+  if (!ignore && threadIdx.x == 0) atomicAdd(loss_sum, lse - x_label);
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const int c = threadIdx.x + k * 256;
@@ -66,11 +76,7 @@ __global__ void __launch_bounds__(256) ce_fwd_bwd_kernel(__nv_bfloat16* __restri
       float f[8], o[8];
       unpack8(raw[k], f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int col = c * 8 + j;
-        o[j] = __expf(f[j] - mx) * inv_s - ((long long)col == y ? gscale : 0.f);
-        if ((long long)col == y) atomicAdd(loss_sum, lse - f[j]);
-      }
+      for (int j = 0; j < 8; ++j) o[j] = f[j] * inv_s - ((long long)(c * 8 + j) == y ? gscale : 0.f);
       st_na_v4(xr + c, pack8(o));
     }
   }

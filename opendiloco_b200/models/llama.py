@@ -234,13 +234,28 @@ class LlamaEngine:
             # ---- attention block (ws.dx is now the gradient of xm = xa + o(att))
             G.mm_tn_acc(ws.dx, ws.att[l], ar.g(p + "self_attn.o_proj.weight"))
             G.mm_nn(ws.dx, ar.w(p + "self_attn.o_proj.weight"), out=ws.datt, b_t=ar.wT(p + "self_attn.o_proj.weight", h, cfg.q_dim))
+            wT_qkv = ar.wT(p + "self_attn.q_proj.weight", cfg.qkv_dim, h)
+            parts_ok = attention_mask is None and wT_qkv is not None and cfg.q_dim % 64 == 0 and cfg.kv_dim % 64 == 0
             if attention_mask is None:
-                A.attention_bwd(ws.datt, ws.qkv[l], ws.att[l], ws.aux[l], ws.dqkv, B, S, Hq, Hkv, D)
+                res = A.attention_bwd(ws.datt, ws.qkv[l], ws.att[l], ws.aux[l], ws.dqkv, B, S, Hq, Hkv, D, want_parts=parts_ok)
             else:
                 _masked_attention_bwd(ws.datt, ws.aux[l], ws.dqkv, B, S, Hq, Hkv, D)
-            K.rope_(ws.dqkv, ws.cos, ws.sin, S, Hq + Hkv, D, backward=True)
-            G.mm_tn_acc(ws.dqkv, ws.xn1[l], ar.qkv_g(l))
-            G.mm_nn(ws.dqkv, ar.qkv_w(l), out=ws.dn, b_t=ar.wT(p + "self_attn.q_proj.weight", cfg.qkv_dim, h))
+                res = ws.dqkv
+            if isinstance(res, tuple):
+                # un-packed gradients (cuDNN): rotate dq/dk in place, three wgrads into the row blocks of the fused
+                # QKV gradient, and ONE dgrad GEMM whose A operand is read from the three tensors
+                dq, dk, dv = res
+                K.rope_(dq, ws.cos, ws.sin, S, Hq, D, backward=True)
+                K.rope_(dk, ws.cos, ws.sin, S, Hkv, D, backward=True)
+                gq = ar.qkv_g(l)
+                G.mm_tn_acc(dq, ws.xn1[l], gq[: cfg.q_dim])
+                G.mm_tn_acc(dk, ws.xn1[l], gq[cfg.q_dim: cfg.q_dim + cfg.kv_dim])
+                G.mm_tn_acc(dv, ws.xn1[l], gq[cfg.q_dim + cfg.kv_dim:])
+                TC.linear_a3(dq, dk, dv, wT_qkv, ws.dn)
+            else:
+                K.rope_(ws.dqkv, ws.cos, ws.sin, S, Hq + Hkv, D, backward=True)
+                G.mm_tn_acc(ws.dqkv, ws.xn1[l], ar.qkv_g(l))
+                G.mm_nn(ws.dqkv, ar.qkv_w(l), out=ws.dn, b_t=wT_qkv)
             K.rmsnorm_bwd(ws.dn, ws.xa[l], ar.w(p + "input_layernorm.weight"), ws.rstd1[l], ws.dx, ws.dx,
                           ar.g(p + "input_layernorm.weight"))
             ws.att[l] = None

@@ -70,8 +70,9 @@ def attention_fwd(qkv: torch.Tensor, B: int, S: int, Hq: int, Hkv: int, D: int):
 
 
 def attention_bwd(dout: torch.Tensor, qkv: torch.Tensor, out: torch.Tensor, aux, dqkv: torch.Tensor, B: int, S: int,
-                  Hq: int, Hkv: int, D: int) -> torch.Tensor:
-    """Writes dq|dk|dv into the packed ``dqkv`` buffer (same layout as qkv)."""
+                  Hq: int, Hkv: int, D: int, want_parts: bool = False):
+    """Writes dq|dk|dv into the packed ``dqkv`` buffer (same layout as qkv) and returns it - or, with ``want_parts`` and a
+    back-end that produces separate dense gradients, returns the tuple (dq [T,Hq*D], dk [T,Hkv*D], dv [T,Hkv*D])."""
     q, k, v = split_qkv(qkv, B, S, Hq, Hkv, D)
     dq, dk, dv = split_qkv(dqkv, B, S, Hq, Hkv, D)
     scale = 1.0 / math.sqrt(D)
@@ -81,6 +82,12 @@ def attention_bwd(dout: torch.Tensor, qkv: torch.Tensor, out: torch.Tensor, aux,
         g = torch.ops.aten._scaled_dot_product_cudnn_attention_backward(
             dout.view(B, S, Hq, D).transpose(1, 2), q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), r[0], r[1], r[6],
             r[7], None, r[2], r[3], r[4], r[5], 0.0, True, scale=scale)
+        if want_parts:
+            # cuDNN hands back three dense [B,S,H,D] tensors: give them to the caller as [T, H*D] matrices instead of
+            # spending three strided copies on packing them (the dgrad GEMM reads its A operand from three tensors)
+            parts = [t.transpose(1, 2) for t in g[:3]]
+            if all(t.is_contiguous() for t in parts):
+                return parts[0].reshape(B * S, Hq * D), parts[1].reshape(B * S, Hkv * D), parts[2].reshape(B * S, Hkv * D)
         dq.copy_(g[0].transpose(1, 2))
         dk.copy_(g[1].transpose(1, 2))
         dv.copy_(g[2].transpose(1, 2))

@@ -23,6 +23,9 @@ _lib.register_optional("odb_gemm_qkv_rope", [c_void_p, c_void_p, c_void_p, c_int
 for _n in ("odb_gemm2_bf16_tn", "odb_gemm2_swiglu", "odb_gemm2_qkv_rope"):
     _lib.register_optional(_n, _lib._OPTIONAL_SIGS[_n.replace("gemm2", "gemm")])
 
+_lib.register_optional("odb_gemm2_bf16_tn_a3", [c_void_p, c_void_p, c_void_p, c_ll, c_ll, c_ll, c_int, c_int, c_int, c_void_p, c_void_p,
+                                               c_int, c_int, c_ll, c_ll, c_void_p])
+
 ENABLED = os.environ.get("ODB_TC_GEMM", "1") != "0"
 TWO_CTA = os.environ.get("ODB_TC_GEMM_2CTA", "1") != "0"     # CTA-pair (cta_group::2, 256x256 tiles) kernels
 
@@ -68,3 +71,14 @@ def linear_qkv_rope(x: torch.Tensor, w: torch.Tensor, qkv: torch.Tensor, cos: to
     _lib.check(_fn("odb_gemm_qkv_rope", M, N)(x.data_ptr(), w.data_ptr(), qkv.data_ptr(), M, N, K, S, rope_cols, cos.data_ptr(),
                                                  sin.data_ptr(), _lib.stream_ptr(x)), "gemm_qkv_rope")
     _lib.count_launch()
+
+
+def linear_a3(a0: torch.Tensor, a1: torch.Tensor, a2: torch.Tensor, w: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out = cat([a0, a1, a2], dim=1) @ w^T with the three A pieces read in place (dq|dk|dv -> dgrad of the fused QKV)."""
+    M = a0.shape[0]
+    N = w.shape[0]
+    _lib.check(_lib.cuda_lib().odb_gemm2_bf16_tn_a3(a0.data_ptr(), a1.data_ptr(), a2.data_ptr(), a0.stride(0), a1.stride(0),
+                                                    a2.stride(0), a0.shape[1], a1.shape[1], a2.shape[1], w.data_ptr(), out.data_ptr(),
+                                                    M, N, w.stride(0), out.stride(0), _lib.stream_ptr(out)), "gemm2_bf16_tn_a3")
+    _lib.count_launch()
+    return out
