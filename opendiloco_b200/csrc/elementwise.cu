@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const __nv_bfloat16* x
 // If dres_in == nullptr the kernel writes dres = dx (used for the final norm, where no skip path exists).
 // Each warp keeps per-lane dw partial sums in registers across its rows; one smem reduction + atomics per CTA.
 template <int NCH, bool kRegAcc>
-__global__ void __launch_bounds__(256, (NCH <= 4) ? 3 : 1) rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+__global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
                                                           const __nv_bfloat16* __restrict__ x,
                                                           const __nv_bfloat16* __restrict__ w,
                                                           const float* __restrict__ rstd,

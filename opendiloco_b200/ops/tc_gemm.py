@@ -26,6 +26,9 @@ for _n in ("odb_gemm2_bf16_tn", "odb_gemm2_swiglu", "odb_gemm2_qkv_rope"):
 _lib.register_optional("odb_gemm2_bf16_tn_a3", [c_void_p, c_void_p, c_void_p, c_ll, c_ll, c_ll, c_int, c_int, c_int, c_void_p, c_void_p,
                                                c_int, c_int, c_ll, c_ll, c_void_p])
 
+_lib.register_optional("odb_wgrad_bf16", [c_void_p, c_void_p, c_void_p, c_ll, c_ll, c_ll, c_int, c_int, c_int, c_void_p, c_ll, c_void_p,
+                                         c_ll, c_int, c_int, c_void_p])
+
 ENABLED = os.environ.get("ODB_TC_GEMM", "1") != "0"
 TWO_CTA = os.environ.get("ODB_TC_GEMM_2CTA", "1") != "0"     # CTA-pair (cta_group::2, 256x256 tiles) kernels
 
@@ -82,3 +85,27 @@ def linear_a3(a0: torch.Tensor, a1: torch.Tensor, a2: torch.Tensor, w: torch.Ten
                                                     M, N, w.stride(0), out.stride(0), _lib.stream_ptr(out)), "gemm2_bf16_tn_a3")
     _lib.count_launch()
     return out
+
+
+WGRAD = os.environ.get("ODB_TC_WGRAD", "1") != "0"
+
+
+def wgrad_usable(*tensors: torch.Tensor) -> bool:
+    return WGRAD and usable(*tensors) and _lib.has_symbol("odb_wgrad_bf16")
+
+
+def wgrad_acc(dy, x: torch.Tensor, dw: torch.Tensor) -> None:
+    """dw (fp32 [N_out, K_out]) += dy^T @ x, reduction over tokens.  ``dy`` is one [T, N_out] matrix or a tuple of up to
+    three matrices whose columns are concatenated (dq | dk | dv; every piece a multiple of 256 columns)."""
+    parts = list(dy) if isinstance(dy, (tuple, list)) else [dy]
+    assert 1 <= len(parts) <= 3 and dw.dtype == torch.float32 and dw.stride(1) == 1
+    T, K_out = x.shape
+    while len(parts) < 3:
+        parts.append(None)
+    ptr = lambda t: t.data_ptr() if t is not None else None   # noqa: E731
+    ld = lambda t: t.stride(0) if t is not None else 0        # noqa: E731
+    nc = lambda t: t.shape[1] if t is not None else 0         # noqa: E731
+    _lib.check(_lib.cuda_lib().odb_wgrad_bf16(ptr(parts[0]), ptr(parts[1]), ptr(parts[2]), ld(parts[0]), ld(parts[1]), ld(parts[2]),
+                                              nc(parts[0]), nc(parts[1]), nc(parts[2]), x.data_ptr(), x.stride(0), dw.data_ptr(),
+                                              dw.stride(0), T, K_out, _lib.stream_ptr(x)), "wgrad_bf16")
+    _lib.count_launch()
