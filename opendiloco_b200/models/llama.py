@@ -248,9 +248,12 @@ class LlamaEngine:
                 K.rope_(dq, ws.cos, ws.sin, S, Hq, D, backward=True)
                 K.rope_(dk, ws.cos, ws.sin, S, Hkv, D, backward=True)
                 gq = ar.qkv_g(l)
-                G.mm_tn_acc(dq, ws.xn1[l], gq[: cfg.q_dim])
-                G.mm_tn_acc(dk, ws.xn1[l], gq[cfg.q_dim: cfg.q_dim + cfg.kv_dim])
-                G.mm_tn_acc(dv, ws.xn1[l], gq[cfg.q_dim + cfg.kv_dim:])
+                if cfg.q_dim % 256 == 0 and cfg.kv_dim % 256 == 0 and TC.wgrad_usable(dq, dk, dv, ws.xn1[l]):
+                    TC.wgrad_acc((dq, dk, dv), ws.xn1[l], gq)          # one launch, A read from the three tensors
+                else:
+                    G.mm_tn_acc(dq, ws.xn1[l], gq[: cfg.q_dim])
+                    G.mm_tn_acc(dk, ws.xn1[l], gq[cfg.q_dim: cfg.q_dim + cfg.kv_dim])
+                    G.mm_tn_acc(dv, ws.xn1[l], gq[cfg.q_dim + cfg.kv_dim:])
                 TC.linear_a3(dq, dk, dv, wT_qkv, ws.dn)
             else:
                 K.rope_(ws.dqkv, ws.cos, ws.sin, S, Hq + Hkv, D, backward=True)

@@ -68,3 +68,27 @@ def test_qkv_rope_epilogue(two_cta, B, S, Hq, Hkv, Kd):
     T.linear_qkv_rope(x, w, out, cos, sin, S, (Hq + Hkv) * 64)
     assert rel(out, ref) < 1e-3
     assert torch.equal(out[:, (Hq + Hkv) * 64:], v_ref)   # v is not rotated
+
+
+@pytest.mark.parametrize("Tn,N,Kd", [(512, 256, 256), (1000, 520, 136), (4096, 1024, 2688), (32768, 768, 512)])
+def test_wgrad_accumulates_in_fp32(Tn, N, Kd):
+    torch.manual_seed(4)
+    dy = torch.randn(Tn, N, device="cuda").to(BF)
+    x = torch.randn(Tn, Kd, device="cuda").to(BF)
+    acc = torch.randn(N, Kd, device="cuda")
+    ref = acc.double() + dy.double().t() @ x.double()
+    T.wgrad_acc(dy, x, acc)
+    assert rel(acc, ref) < 2e-5
+    T.wgrad_acc(dy, x, acc)                                  # accumulation across calls (micro-batches)
+    assert rel(acc, ref + dy.double().t() @ x.double()) < 2e-5
+
+
+def test_wgrad_three_sources_and_views():
+    torch.manual_seed(5)
+    Tn, Kd = 2048, 512
+    dq, dk, dv = (torch.randn(Tn, n, device="cuda").to(BF) for n in (512, 256, 256))
+    x = torch.randn(Tn, Kd, device="cuda").to(BF)
+    big = torch.zeros(1024 + 256, Kd, device="cuda")
+    T.wgrad_acc((dq, dk, dv), x, big[:1024])
+    ref = torch.cat([dq, dk, dv], 1).double().t() @ x.double()
+    assert rel(big[:1024], ref) < 2e-5 and torch.count_nonzero(big[1024:]) == 0
