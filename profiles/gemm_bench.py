@@ -59,16 +59,16 @@ for (Tn, N, Kd) in [(512, 256, 256), (1000, 520, 136), (32768, 1024, 1024), (327
                     (8192, 32000, 1024), (16384, 2560, 2048)]:
     dy = torch.randn(Tn, N, device=dev).to(BF); x = torch.randn(Tn, Kd, device=dev).to(BF)
     acc0 = torch.randn(N, Kd, device=dev)
-    ref = acc0.clone(); G.mm_tn_acc(dy, x, ref)
+    ref = acc0 + dy.float().t() @ x.float()
     out = acc0.clone(); T.wgrad_acc(dy, x, out); torch.cuda.synchronize()
     err = rel(out, ref)
     scratch = acc0.clone()
-    t1 = timeit(lambda: T.wgrad_acc(dy, x, scratch)); t0 = timeit(lambda: G.mm_tn_acc(dy, x, scratch))
+    t1 = timeit(lambda: T.wgrad_acc(dy, x, scratch)); t0 = timeit(lambda: torch.addmm(scratch, dy.t(), x, out_dtype=torch.float32, out=scratch))     # cuBLASLt, fp32 out, beta=1
     fl = 2 * Tn * N * Kd
     print(f"T{Tn} N{N} K{Kd}: rel_err {err:.2e}  ours {t1*1e3:.1f}us {fl/t1/1e9:.0f} TF/s | cublas {t0*1e3:.1f}us {fl/t0/1e9:.0f} TF/s | ratio {t0/t1:.2f}")
 # three-source A (dq|dk|dv)
 Tn, Kd = 32768, 1024
 dq, dk, dv = (torch.randn(Tn, 1024, device=dev).to(BF) for _ in range(3)); x = torch.randn(Tn, Kd, device=dev).to(BF)
-ref = torch.zeros(3072, Kd, device=dev); G.mm_tn_acc(torch.cat([dq, dk, dv], 1), x, ref)
+ref = torch.cat([dq, dk, dv], 1).float().t() @ x.float()
 out = torch.zeros(3072, Kd, device=dev); T.wgrad_acc((dq, dk, dv), x, out); torch.cuda.synchronize()
 print("3-source wgrad rel_err", rel(out, ref), "time", timeit(lambda: T.wgrad_acc((dq, dk, dv), x, out)) * 1e3, "us")
