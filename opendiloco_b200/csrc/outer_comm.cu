@@ -39,6 +39,17 @@ __device__ __forceinline__ void multimem_st_f32x4(void* mc, const float4& v) {
   asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
                :: "l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+// weak (non-.sys) forms: ordering is provided by the explicit barriers around the phase, as in NCCL's NVLS kernels
+__device__ __forceinline__ float4 multimem_ld_reduce_f32x4_weak(const void* mc) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.weak.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(mc) : "memory");
+  return r;
+}
+__device__ __forceinline__ void multimem_st_f32x4_weak(void* mc, const float4& v) {
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 // 8 bf16 values, reduced with fp32 accumulation inside the switch
 __device__ __forceinline__ uint4 multimem_ld_reduce_bf16x8(const void* mc) {
   uint4 r;
@@ -99,7 +110,7 @@ __global__ void __launch_bounds__(512) fused_outer_kernel(float* __restrict__ th
                                                           float* __restrict__ theta_local, __nv_bfloat16* __restrict__ shadow,
                                                           void* sym_local, void* sym_mc, PeerPtrs sym_peers, PeerPtrs flag_ptrs,
                                                           int rank, int world, long long n, float lr, float mu, int nesterov,
-                                                          unsigned seq, int* timeout_flag) {
+                                                          unsigned seq, int* timeout_flag, int p1_ctas, int mm_weak) {
   cg::grid_group grid = cg::this_grid();
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long nthreads = (long long)gridDim.x * blockDim.x;
@@ -125,8 +136,12 @@ __global__ void __launch_bounds__(512) fused_outer_kernel(float* __restrict__ th
   const long long per = (nvec + world - 1) / world;
   const long long lo = per * rank, hi = (lo + per < nvec) ? lo + per : nvec;
   if constexpr (kMultimem) {
-    // 4 independent in-switch reductions in flight per thread before the dependent multicast stores
-    constexpr int U = 4;
+    // U independent in-switch reductions in flight per thread before the dependent multicast stores; only the first
+    // p1_ctas CTAs take part (the NVLink fabric, not the SMs, is the limit of this phase)
+    constexpr int U = 8;
+    const long long nthreads1 = (long long)p1_ctas * blockDim.x;
+    const long long nthreads = nthreads1;
+    if (blockIdx.x < p1_ctas)
     for (long long i0 = lo + tid; i0 < hi; i0 += nthreads * U) {
       if constexpr (kBf16Delta) {
         uint4 s[U];
@@ -151,14 +166,16 @@ __global__ void __launch_bounds__(512) fused_outer_kernel(float* __restrict__ th
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const long long i = i0 + u * nthreads;
-          if (i < hi) s[u] = multimem_ld_reduce_f32x4(reinterpret_cast<const float*>(sym_mc) + i * 4);
+          if (i < hi) s[u] = mm_weak ? multimem_ld_reduce_f32x4_weak(reinterpret_cast<const float*>(sym_mc) + i * 4)
+                                     : multimem_ld_reduce_f32x4(reinterpret_cast<const float*>(sym_mc) + i * 4);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const long long i = i0 + u * nthreads;
           if (i < hi) {
             s[u].x *= inv_world; s[u].y *= inv_world; s[u].z *= inv_world; s[u].w *= inv_world;
-            multimem_st_f32x4(reinterpret_cast<float*>(sym_mc) + i * 4, s[u]);
+            if (mm_weak) multimem_st_f32x4_weak(reinterpret_cast<float*>(sym_mc) + i * 4, s[u]);
+            else multimem_st_f32x4(reinterpret_cast<float*>(sym_mc) + i * 4, s[u]);
           }
         }
       }
@@ -220,7 +237,7 @@ __global__ void __launch_bounds__(512) fused_outer_kernel(float* __restrict__ th
 ODB_EXPORT int odb_fused_outer_step(void* theta_outer, void* buf, void* theta_local, void* shadow, void* sym_local,
                                     void* sym_mc, const void* const* sym_peers, const void* const* flag_ptrs, int rank,
                                     int world, long long n, float lr, float mu, int nesterov, unsigned seq, int delta_bf16,
-                                    void* timeout_flag, cudaStream_t st) {
+                                    void* timeout_flag, int p1_ctas, int mm_weak, cudaStream_t st) {
   if (world > kMaxPeers || n % (8ll * world)) return -1;
   PeerPtrs sp{}, fp{};
   for (int i = 0; i < world; ++i) {
@@ -238,7 +255,8 @@ ODB_EXPORT int odb_fused_outer_step(void* theta_outer, void* buf, void* theta_lo
   const int grid = sm_count() * (per_sm > 2 ? 2 : per_sm);
   float* a0 = (float*)theta_outer; float* a1 = (float*)buf; float* a2 = (float*)theta_local;
   __nv_bfloat16* a3 = (__nv_bfloat16*)shadow; int* tf = (int*)timeout_flag;
-  void* args[] = {&a0, &a1, &a2, &a3, &sym_local, &sym_mc, &sp, &fp, &rank, &world, &n, &lr, &mu, &nesterov, &seq, &tf};
+  if (p1_ctas <= 0 || p1_ctas > grid) p1_ctas = grid;
+  void* args[] = {&a0, &a1, &a2, &a3, &sym_local, &sym_mc, &sp, &fp, &rank, &world, &n, &lr, &mu, &nesterov, &seq, &tf, &p1_ctas, &mm_weak};
   e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(512), args, 0, st);
   return (int)e;
 }

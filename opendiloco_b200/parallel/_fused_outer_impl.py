@@ -17,7 +17,7 @@ from ..utils.logger import get_logger
 
 c_void_p, c_int, c_ll, c_float, c_uint = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_uint
 _lib.register_optional("odb_fused_outer_step", [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                                c_int, c_int, c_ll, c_float, c_float, c_int, c_uint, c_int, c_void_p, c_void_p])
+                                                c_int, c_int, c_ll, c_float, c_float, c_int, c_uint, c_int, c_void_p, c_int, c_int, c_void_p])
 logger = get_logger()
 FLAG_WORDS = 64     # 2 barrier slots x 16 peers, padded
 
@@ -88,7 +88,8 @@ class FusedOuterStep:
             sa.shadow_local.data_ptr() if sa.shadow_local is not None else None, self.window.data_ptr(),
             self.mc_ptr if self.mc_ptr else None, self._win_ptrs, self._flag_ptrs, self.rank, self.world, self.n,
             float(g["lr"]), float(g["momentum"]), int(bool(g.get("nesterov", False))), self.seq, int(self.delta_bf16),
-            self.timeout_flag.data_ptr(), _lib.stream_ptr(sa.theta_outer))
+            self.timeout_flag.data_ptr(), int(os.environ.get("ODB_OUTER_P1_CTAS", 0)), int(os.environ.get("ODB_OUTER_MM_WEAK", 1)),
+            _lib.stream_ptr(sa.theta_outer))
         _lib.check(rc, "fused_outer_step")
         _lib.count_launch()
         self.seq += 2

@@ -30,6 +30,8 @@ from opendiloco_b200.parallel.swarm import DHT  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--models", default="150m,1b")
 ap.add_argument("--iters", type=int, default=5)
+ap.add_argument("--labels", default="fused_fp32,fused_bf16,nccl_flat_fp32,blockwise8bit")
+ap.add_argument("--no-ref", action="store_true")
 a = ap.parse_args()
 
 comm.init_distributed("nccl")
@@ -81,8 +83,11 @@ for name in a.models.split(","):
         outer.zero_grad()
         nonlocal_off[:] = [p.data.detach().clone().to("cpu") for p in params]
 
-    reference_outer()
-    ref_min, ref_med = timed(reference_outer, max(2, a.iters // 2))
+    if a.no_ref:
+        ref_min = float("nan")
+    else:
+        reference_outer()
+        ref_min, ref_med = timed(reference_outer, max(2, a.iters // 2))
     del params, outer, offloaded
     torch.cuda.empty_cache()
 
@@ -90,6 +95,8 @@ for name in a.models.split(","):
     row = {"model": name, "params": P, "n_gpus": world, "reference_ms": ref_min, "reference_GBps": 4 * P / ref_min / 1e6}
     for label, comp, fused in [("fused_fp32", None, True), ("fused_bf16", "bf16", True), ("nccl_flat_fp32", None, False),
                                ("blockwise8bit", "blockwise8bit", False)]:
+        if label not in a.labels.split(","):
+            continue
         flat = torch.nn.Parameter(torch.randn(((P + 16383) // 16384) * 16384, device=dev) * 0.02)
         opt = DiLoCoOptimizer(dht=DHT(start=True), batch_size=1, num_inner_steps=1, params=[flat],
                               outer_optimizer=partial(torch.optim.SGD, lr=0.7, momentum=0.9, nesterov=True),
