@@ -73,6 +73,12 @@ __device__ __forceinline__ float4 ld_vol_f4(const float* p) {
   return make_float4(__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w));
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
@@ -110,13 +116,15 @@ __global__ void __launch_bounds__(512) fused_outer_kernel(float* __restrict__ th
                                                           float* __restrict__ theta_local, __nv_bfloat16* __restrict__ shadow,
                                                           void* sym_local, void* sym_mc, PeerPtrs sym_peers, PeerPtrs flag_ptrs,
                                                           int rank, int world, long long n, float lr, float mu, int nesterov,
-                                                          unsigned seq, int* timeout_flag, int p1_ctas, int mm_weak) {
+                                                          unsigned seq, int* timeout_flag, int p1_ctas, int mm_weak, unsigned long long* stamps) {
   cg::grid_group grid = cg::this_grid();
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long nthreads = (long long)gridDim.x * blockDim.x;
   constexpr int VEC = kBf16Delta ? 8 : 4;         // elements per 16-byte vector of the delta window
   const long long nvec = n / VEC;
 
+  const bool stamp = stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  if (stamp) stamps[0] = globaltimer_ns();
   // ---------------- phase 0: pseudo-gradient into the local symmetric window
   for (long long i = tid; i < nvec; i += nthreads) {
     if constexpr (kBf16Delta) {
@@ -129,7 +137,9 @@ __global__ void __launch_bounds__(512) fused_outer_kernel(float* __restrict__ th
       st_f4(reinterpret_cast<float*>(sym_local) + i * 4, make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w));
     }
   }
+  if (stamp) stamps[1] = globaltimer_ns();
   world_barrier(grid, flag_ptrs, rank, world, seq, 0, timeout_flag);
+  if (stamp) stamps[2] = globaltimer_ns();
 
   // ---------------- phase 1: reduce my slice across ranks, publish the mean to every rank
   const float inv_world = 1.f / (float)world;
@@ -204,7 +214,9 @@ __global__ void __launch_bounds__(512) fused_outer_kernel(float* __restrict__ th
       }
     }
   }
+  if (stamp) stamps[3] = globaltimer_ns();
   world_barrier(grid, flag_ptrs, rank, world, seq + 1, 1, timeout_flag);
+  if (stamp) stamps[4] = globaltimer_ns();
 
   // ---------------- phase 2: SGD-Nesterov on the whole vector from the (now averaged) local window
   for (long long i = tid; i < n / 4; i += nthreads) {
@@ -231,13 +243,14 @@ __global__ void __launch_bounds__(512) fused_outer_kernel(float* __restrict__ th
     st_f4(theta_local + i * 4, to);
     if (shadow) *reinterpret_cast<uint2*>(shadow + i * 4) = make_uint2(f2_to_bf2(to.x, to.y), f2_to_bf2(to.z, to.w));
   }
+  if (stamp) stamps[5] = globaltimer_ns();   // block 0's own end (other CTAs may still be in phase 2)
 }
 
 // n must be a multiple of 8*world (flat arenas are padded to 16384).  Returns 0, a cudaError, or -3 if co-residency fails.
 ODB_EXPORT int odb_fused_outer_step(void* theta_outer, void* buf, void* theta_local, void* shadow, void* sym_local,
                                     void* sym_mc, const void* const* sym_peers, const void* const* flag_ptrs, int rank,
                                     int world, long long n, float lr, float mu, int nesterov, unsigned seq, int delta_bf16,
-                                    void* timeout_flag, int p1_ctas, int mm_weak, cudaStream_t st) {
+                                    void* timeout_flag, int p1_ctas, int mm_weak, void* stamps, cudaStream_t st) {
   if (world > kMaxPeers || n % (8ll * world)) return -1;
   PeerPtrs sp{}, fp{};
   for (int i = 0; i < world; ++i) {
@@ -256,7 +269,7 @@ ODB_EXPORT int odb_fused_outer_step(void* theta_outer, void* buf, void* theta_lo
   float* a0 = (float*)theta_outer; float* a1 = (float*)buf; float* a2 = (float*)theta_local;
   __nv_bfloat16* a3 = (__nv_bfloat16*)shadow; int* tf = (int*)timeout_flag;
   if (p1_ctas <= 0 || p1_ctas > grid) p1_ctas = grid;
-  void* args[] = {&a0, &a1, &a2, &a3, &sym_local, &sym_mc, &sp, &fp, &rank, &world, &n, &lr, &mu, &nesterov, &seq, &tf, &p1_ctas, &mm_weak};
+  void* args[] = {&a0, &a1, &a2, &a3, &sym_local, &sym_mc, &sp, &fp, &rank, &world, &n, &lr, &mu, &nesterov, &seq, &tf, &p1_ctas, &mm_weak, &stamps};
   e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(512), args, 0, st);
   return (int)e;
 }

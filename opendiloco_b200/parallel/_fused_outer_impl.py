@@ -17,7 +17,7 @@ from ..utils.logger import get_logger
 
 c_void_p, c_int, c_ll, c_float, c_uint = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_uint
 _lib.register_optional("odb_fused_outer_step", [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                                c_int, c_int, c_ll, c_float, c_float, c_int, c_uint, c_int, c_void_p, c_int, c_int, c_void_p])
+                                                c_int, c_int, c_ll, c_float, c_float, c_int, c_uint, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p])
 logger = get_logger()
 FLAG_WORDS = 64     # 2 barrier slots x 16 peers, padded
 
@@ -54,6 +54,8 @@ class FusedOuterStep:
         self._win_ptrs = PtrArr(*[int(p) for p in self.h_win.buffer_ptrs])
         self._flag_ptrs = PtrArr(*[int(p) for p in self.h_flag.buffer_ptrs])
         self.timeout_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        # ODB_OUTER_STAMPS=1: block 0 records globaltimer at the phase boundaries (phase profile of the fused kernel)
+        self.stamps = torch.zeros(8, dtype=torch.int64, device=dev) if os.environ.get("ODB_OUTER_STAMPS") else None
         self.seq = 1
         torch.cuda.synchronize(dev)
         self.h_flag.barrier()
@@ -89,11 +91,18 @@ class FusedOuterStep:
             self.mc_ptr if self.mc_ptr else None, self._win_ptrs, self._flag_ptrs, self.rank, self.world, self.n,
             float(g["lr"]), float(g["momentum"]), int(bool(g.get("nesterov", False))), self.seq, int(self.delta_bf16),
             self.timeout_flag.data_ptr(), int(os.environ.get("ODB_OUTER_P1_CTAS", 0)), int(os.environ.get("ODB_OUTER_MM_WEAK", 1)),
-            _lib.stream_ptr(sa.theta_outer))
+            self.stamps.data_ptr() if self.stamps is not None else None, _lib.stream_ptr(sa.theta_outer))
         _lib.check(rc, "fused_outer_step")
         _lib.count_launch()
         self.seq += 2
         sa.fv.gather_compute_weights()
+
+    def phase_times_us(self) -> dict | None:
+        if self.stamps is None:
+            return None
+        t = self.stamps.cpu().tolist()
+        return {"phase0_delta": (t[1] - t[0]) / 1e3, "barrier0": (t[2] - t[1]) / 1e3, "phase1_reduce_bcast": (t[3] - t[2]) / 1e3,
+                "barrier1": (t[4] - t[3]) / 1e3, "phase2_nesterov(block0)": (t[5] - t[4]) / 1e3}
 
     def check_timeout(self) -> bool:
         return bool(self.timeout_flag.item())

@@ -117,6 +117,8 @@ for name in a.models.split(","):
         row[label + "_ms"] = t
         row[label + "_GBps"] = 4 * P / t / 1e6
         row[label + "_fused_kernel"] = used
+        if used and opt._fused.phase_times_us() is not None:
+            row[label + "_phases_us"] = opt._fused.phase_times_us()
         opt.shutdown()
         del opt, flat
         torch.cuda.empty_cache()

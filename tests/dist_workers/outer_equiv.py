@@ -87,7 +87,7 @@ if cuda:
     cases += [("fused_fp32", None, True), ("fused_bf16", "bf16", True)]
 cases += [(c, c, False) for c in ("fp16", "bf16", "scaled-fp16", "uniform8bit", "quantile8bit", "blockwise8bit")]
 tol = {"flat": 2e-6, "fused_fp32": 2e-6, "fused_bf16": 2e-3, "fp16": 1e-3, "bf16": 3e-3, "scaled-fp16": 1e-3,
-       "uniform8bit": 3e-2, "quantile8bit": 6e-2, "blockwise8bit": 2e-2}
+       "uniform8bit": 8e-2, "quantile8bit": 8e-2, "blockwise8bit": 2e-2}
 ok = True
 for name, comp, fused in cases:
     out, used = ours(comp, fused)
