@@ -18,8 +18,12 @@ from ..utils.logger import get_logger
 c_void_p, c_int, c_ll, c_float, c_uint = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_uint
 _lib.register_optional("odb_fused_outer_step", [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                                 c_int, c_int, c_ll, c_float, c_float, c_int, c_uint, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p])
+_lib.register_optional("odb_fused_outer_pipelined", [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                                    c_ll, c_float, c_float, c_int, c_uint, c_uint, c_int, c_int, c_int, c_void_p,
+                                                    c_void_p, c_void_p])
 logger = get_logger()
-FLAG_WORDS = 64     # 2 barrier slots x 16 peers, padded
+MAX_CHUNKS, MAX_PEERS = 64, 16
+FLAG_WORDS = 2 * MAX_CHUNKS * MAX_PEERS     # pipelined kernel: ready[chunk][peer] | done[chunk][peer]; phase-sequential kernel uses the first 32
 
 
 class FusedOuterStep:
@@ -57,10 +61,18 @@ class FusedOuterStep:
         # ODB_OUTER_STAMPS=1: block 0 records globaltimer at the phase boundaries (phase profile of the fused kernel)
         self.stamps = torch.zeros(8, dtype=torch.int64, device=dev) if os.environ.get("ODB_OUTER_STAMPS") else None
         self.seq = 1
+        self.launch_idx = 0
+        self.counters = torch.zeros(2 * MAX_CHUNKS, dtype=torch.int32, device=dev)
+        self.nchunk = int(os.environ.get("ODB_OUTER_CHUNKS", 16))
+        while self.n % (8 * self.world * self.nchunk):
+            self.nchunk //= 2
+        self.pipelined = bool(self.mc_ptr) and self.nchunk >= 2 and os.environ.get("ODB_OUTER_PIPELINED", "1") != "0" \
+            and _lib.has_symbol("odb_fused_outer_pipelined")
         torch.cuda.synchronize(dev)
         self.h_flag.barrier()
         logger.info(f"fused outer step: {self.world} ranks, window {self.n * self.window.element_size() / 1e6:.0f} MB "
-                    f"{'bf16' if delta_bf16 else 'fp32'}, multimem={'yes' if self.mc_ptr else 'no (P2P loads/stores)'}")
+                    f"{'bf16' if delta_bf16 else 'fp32'}, multimem={'yes' if self.mc_ptr else 'no (P2P loads/stores)'}, "
+                    f"{'pipelined x' + str(self.nchunk) if self.pipelined else 'phase-sequential'}")
 
     @classmethod
     def try_create(cls, opt, compression=None):
@@ -85,6 +97,20 @@ class FusedOuterStep:
         sa = self.sa
         g = sa._sgd_hparams()
         lib = _lib.cuda_lib()
+        if self.pipelined:
+            self.launch_idx += 1
+            rc = lib.odb_fused_outer_pipelined(
+                sa.theta_outer.data_ptr(), sa.momentum_buffer.data_ptr(), sa.theta_local.data_ptr(),
+                sa.shadow_local.data_ptr() if sa.shadow_local is not None else None, self.window.data_ptr(), self.mc_ptr,
+                self._flag_ptrs, self.rank, self.world, self.n, float(g["lr"]), float(g["momentum"]),
+                int(bool(g.get("nesterov", False))), self.seq, self.launch_idx, self.nchunk,
+                int(os.environ.get("ODB_OUTER_COMM_CTAS", 0)), int(self.delta_bf16), self.counters.data_ptr(),
+                self.timeout_flag.data_ptr(), _lib.stream_ptr(sa.theta_outer))
+            _lib.check(rc, "fused_outer_pipelined")
+            _lib.count_launch()
+            self.seq += 2
+            sa.fv.gather_compute_weights()
+            return
         rc = lib.odb_fused_outer_step(
             sa.theta_outer.data_ptr(), sa.momentum_buffer.data_ptr(), sa.theta_local.data_ptr(),
             sa.shadow_local.data_ptr() if sa.shadow_local is not None else None, self.window.data_ptr(),
