@@ -646,13 +646,16 @@ class DiLoCoOptimizer:
             else self.matchmaking_time
         deadline = time.perf_counter() + float(budget)
         keys = [key(r) for r in range(n)]
+        t_start = time.perf_counter()
         while time.perf_counter() < deadline:
             try:
                 if store.check(keys):
                     return None
             except Exception:
                 return None
-            time.sleep(0.005)
+            # workers of a healthy swarm arrive within microseconds of each other: spin first, back off later
+            if time.perf_counter() - t_start > 0.002:
+                time.sleep(0.0005)
         present = [r for r in range(n) if store.check([key(r)])]
         logger.log(self.status_loglevel, f"Timeout waiting for peers, going to skip slowest peers; present={present}")
         return present
