@@ -1,0 +1,253 @@
+// Causal flash-attention forward on tcgen05 / TMEM / TMA for sm_100a, head_dim 64, bf16, MHA + GQA.
+//
+// Reads q/k/v straight out of the packed projection buffer qkv[T, (Hq + 2*Hkv) * 64] (token-major rows: no transposes)
+// through ONE tensor map, writes out[T, Hq*64] token-major (the o-proj GEMM's A operand) and lse[B, Hq, S].
+//
+// One CTA per (batch, q-head, 128-query block); two CTAs co-reside per SM (112 KB smem, 256 TMEM columns each) so one
+// CTA's softmax overlaps the other's MMAs.  192 threads:
+//   warp 0     TMA: Q once, then K_j / V_j 128-key tiles through a 2-stage mbarrier ring
+//   warp 1     MMA: S = Q K_j^T  (tcgen05.mma M128 N128 K16 x4, both operands K-major, accumulator S in TMEM)
+//                   O += P V_j   (M128 N64 K16 x8; A = P from shared memory K-major, B = V_j tile MN-major)
+//   warps 2-5  softmax: one query row per thread (TMEM lane == row): tcgen05.ld S, online max/sum with exp2, causal mask
+//              on the diagonal tile, rescale O in TMEM (tcgen05.ld/st), write P (bf16) into the swizzled smem operand;
+//              epilogue: O / l -> bf16 -> swizzled staging tile -> TMA store
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+using namespace odb;
+using namespace sm100;
+
+namespace attn {
+
+constexpr int BQ = 128, BKV = 128, D = 64;
+constexpr int TILE_BYTES = 128 * 128;           // a [128 x 64] bf16 tile (128-byte rows)
+constexpr int THREADS = 192;
+constexpr int SMEM_BYTES = TILE_BYTES /*Q*/ + 2 * TILE_BYTES /*K*/ + 2 * TILE_BYTES /*V*/ + 2 * TILE_BYTES /*P*/ + 1024 + 256;
+constexpr uint32_t TMEM_COLS = 256;             // S: [0,128)  O: [128,192)
+
+struct Params {
+  int B, S, Hq, Hkv;
+  float scale_log2;        // softmax_scale * log2(e)
+  float* lse;              // [B, Hq, S], natural log
+};
+
+__global__ void __launch_bounds__(THREADS, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out, Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + TILE_BYTES;
+  uint8_t* sV = sK + 2 * TILE_BYTES;
+  uint8_t* sP = sV + 2 * TILE_BYTES;            // two 64-key chunks of [128 rows x 128 B]
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(sP + 2 * TILE_BYTES);
+  uint64_t* kv_full = q_full + 1;               // [2]
+  uint64_t* kv_empty = kv_full + 2;             // [2]
+  uint64_t* s_full = kv_empty + 2;
+  uint64_t* p_full = s_full + 1;
+  uint64_t* o_done = p_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nq = p.S / BQ;
+  const int qblk = nq - 1 - (int)blockIdx.x;    // longest (most KV tiles) first
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int hk = h / (p.Hq / p.Hkv);
+  const int nkv = qblk + 1;                     // causal: key tiles 0..qblk
+  const int row0 = b * p.S + qblk * BQ;         // first token row of this query tile
+  const int col_q = h * D, col_k = (p.Hq + hk) * D, col_v = (p.Hq + p.Hkv + hk) * D;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_out);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);      // one arrival per softmax warp
+    mbar_init(o_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, TILE_BYTES);
+      tma_load_2d(sQ, &tmap_qkv, q_full, col_q, row0);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[st], 2 * TILE_BYTES);
+        tma_load_2d(sK + st * TILE_BYTES, &tmap_qkv, &kv_full[st], col_k, b * p.S + j * BKV);
+        tma_load_2d(sV + st * TILE_BYTES, &tmap_qkv, &kv_full[st], col_v, b * p.S + j * BKV);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);   // S[128,128] = Q (K-major) x K^T (K-major)
+    constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, D, 0, 1);     // O[128,64] = P (K-major) x V (MN-major)
+    mbar_wait(q_full, 0);
+    for (int j = 0; j < nkv; ++j) {
+      const int st = j & 1;
+      mbar_wait(&kv_full[st], (j >> 1) & 1);
+      tc_fence_after_sync();
+      if (elect_one()) {
+        const uint64_t qd = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+        const uint64_t kd = make_smem_desc_sw128(smem_u32(sK + st * TILE_BYTES), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) umma_ss(tS, qd + 2 * k, kd + 2 * k, idesc_qk, k > 0);
+        umma_commit(s_full);
+      }
+      __syncwarp();
+      mbar_wait(p_full, j & 1);                  // P_j in smem, O rescaled, S_j consumed
+      tc_fence_after_sync();
+      if (elect_one()) {
+        const uint64_t vd = make_smem_desc_sw128(smem_u32(sV + st * TILE_BYTES), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k) {
+          const uint64_t pd = make_smem_desc_sw128(smem_u32(sP + (k >> 2) * TILE_BYTES) + (k & 3) * 32, 16, 1024);
+          umma_ss(tO, pd, vd + 128 * k, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&kv_empty[st]);              // K_j / V_j stage reusable
+        umma_commit(o_done);                     // O (and the P buffer) stable
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax / correction / epilogue
+    const int q = warp & 3;
+    const int row = q * 32 + lane;               // query row inside the tile == TMEM lane
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    float m = -INFINITY, l = 0.f;
+    const float c = p.scale_log2;
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after_sync();
+      const bool diag = (j == qblk);
+      // pass A: row maximum
+      float mx = m;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tS + lane_off + cc * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float v = __uint_as_float(r[i]);
+          if (diag && (cc * 32 + i) > row) v = -INFINITY;
+          mx = fmaxf(mx, v);
+        }
+      }
+      const float alpha = exp2f((m - mx) * c);   // m = -inf on the first tile -> 0
+      const float mc = mx * c;
+      // pass B: probabilities (kept packed in registers until the P buffer is free)
+      uint32_t pk[64];
+      float sum = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tS + lane_off + cc * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float v0 = __uint_as_float(r[i]), v1 = __uint_as_float(r[i + 1]);
+          float p0 = exp2f(v0 * c - mc), p1 = exp2f(v1 * c - mc);
+          if (diag) {
+            if ((cc * 32 + i) > row) p0 = 0.f;
+            if ((cc * 32 + i + 1) > row) p1 = 0.f;
+          }
+          sum += p0 + p1;
+          pk[cc * 16 + i / 2] = f2_to_bf2(p0, p1);
+        }
+      }
+      l = l * alpha + sum;
+      m = mx;
+      if (j > 0) {
+        mbar_wait(o_done, (j - 1) & 1);          // PV_{j-1} retired: O is stable, the P buffer is free
+        tc_fence_after_sync();
+        // rescale the running output
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tO + lane_off + cc * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+          tmem_st_32x32b_x32(tO + lane_off + cc * 32, r);
+        }
+        tmem_st_wait();
+      }
+      // P -> shared memory, K-major 128-byte-swizzled operand: chunk (keys/64), row r, 16-byte unit u at (u ^ (r & 7))
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        uint8_t* dst = sP + (u >> 3) * TILE_BYTES + row * 128 + (((u & 7) ^ (row & 7)) * 16);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(pk[u * 4 + 0], pk[u * 4 + 1], pk[u * 4 + 2], pk[u * 4 + 3]);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // ---- epilogue
+    mbar_wait(o_done, (nkv - 1) & 1);
+    tc_fence_after_sync();
+    const float inv_l = 1.f / l;
+    float o[64];
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tO + lane_off + cc * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[cc * 32 + i] = __uint_as_float(r[i]) * inv_l;
+    }
+    uint8_t* stg = sP;                           // P buffer is free now: reuse its first chunk as the output staging tile
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float f[8] = {o[u * 8 + 0], o[u * 8 + 1], o[u * 8 + 2], o[u * 8 + 3], o[u * 8 + 4], o[u * 8 + 5], o[u * 8 + 6], o[u * 8 + 7]};
+      *reinterpret_cast<uint4*>(stg + row * 128 + ((u ^ (row & 7)) * 16)) = pack8(f);
+    }
+    p.lse[((size_t)b * p.Hq + h) * p.S + qblk * BQ + row] = (m * c + log2f(l)) * 0.6931471805599453f;
+    fence_proxy_async_smem();
+    named_bar_sync(1, 128);
+    if (threadIdx.x == 64) {
+      tma_store_2d(&tmap_out, stg, col_q, row0);
+      tma_store_commit();
+      tma_store_wait<0>();
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+}  // namespace attn
+
+// qkv: [B*S, (Hq+2*Hkv)*64] bf16 (row stride ld_qkv elements); out: [B*S, Hq*64] bf16; lse: [B, Hq, S] fp32
+ODB_EXPORT int odb_attn_fwd(const void* qkv, void* out, void* lse, int B, int S, int Hq, int Hkv, long long ld_qkv,
+                            long long ld_out, float softmax_scale, cudaStream_t st) {
+  using namespace attn;
+  if (S % BQ || Hq % Hkv || ld_qkv % 8 || ld_out % 8) return -1;
+  CUtensorMap tq, to;
+  int rc;
+  const long long T = (long long)B * S;
+  if ((rc = make_tmap_2d(&tq, qkv, T, (Hq + 2 * Hkv) * D, ld_qkv * 2, 128, 64, 2))) return rc;
+  if ((rc = make_tmap_2d(&to, out, T, Hq * D, ld_out * 2, 128, 64, 2))) return rc;
+  Params p{};
+  p.B = B; p.S = S; p.Hq = Hq; p.Hkv = Hkv;
+  p.scale_log2 = softmax_scale * 1.4426950408889634f;
+  p.lse = (float*)lse;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  dim3 grid(S / BQ, Hq, B);
+  attn_fwd_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tq, to, p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
