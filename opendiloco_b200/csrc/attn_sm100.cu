@@ -25,6 +25,12 @@ constexpr int THREADS = 192;
 constexpr int SMEM_BYTES = TILE_BYTES /*Q*/ + 2 * TILE_BYTES /*K*/ + 2 * TILE_BYTES /*V*/ + 2 * TILE_BYTES /*P*/ + 1024 + 256;
 constexpr uint32_t TMEM_COLS = 256;             // S: [0,128)  O: [128,192)
 
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct Params {
   int B, S, Hq, Hkv;
   float scale_log2;        // softmax_scale * log2(e)
@@ -126,58 +132,59 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       mbar_wait(s_full, j & 1);
       tc_fence_after_sync();
       const bool diag = (j == qblk);
-      // pass A: row maximum
-      float mx = m;
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tS + lane_off + cc * 32, r);
-        tmem_ld_wait();
+      // the whole S row of this thread in one go: four TMEM loads in flight, a single wait
+      uint32_t sr[128];
+      tmem_ld_32x32b_x32(tS + lane_off + 0, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
+      tmem_ld_32x32b_x32(tS + lane_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
+      tmem_ld_32x32b_x32(tS + lane_off + 64, *reinterpret_cast<uint32_t(*)[32]>(&sr[64]));
+      tmem_ld_32x32b_x32(tS + lane_off + 96, *reinterpret_cast<uint32_t(*)[32]>(&sr[96]));
+      tmem_ld_wait();
+      if (diag) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float v = __uint_as_float(r[i]);
-          if (diag && (cc * 32 + i) > row) v = -INFINITY;
-          mx = fmaxf(mx, v);
-        }
+        for (int i = 0; i < 128; ++i)
+          if (i > row) sr[i] = 0xff800000u;      // -inf
       }
-      const float alpha = exp2f((m - mx) * c);   // m = -inf on the first tile -> 0
+      float mx4[4] = {m, m, m, m};               // four independent chains instead of one 128-deep dependency
+#pragma unroll
+      for (int i = 0; i < 128; i += 4) {
+        mx4[0] = fmaxf(mx4[0], __uint_as_float(sr[i]));
+        mx4[1] = fmaxf(mx4[1], __uint_as_float(sr[i + 1]));
+        mx4[2] = fmaxf(mx4[2], __uint_as_float(sr[i + 2]));
+        mx4[3] = fmaxf(mx4[3], __uint_as_float(sr[i + 3]));
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      const float alpha = fast_exp2((m - mx) * c);   // m = -inf on the first tile -> 0
       const float mc = mx * c;
-      // pass B: probabilities (kept packed in registers until the P buffer is free)
       uint32_t pk[64];
-      float sum = 0.f;
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tS + lane_off + cc * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float v0 = __uint_as_float(r[i]), v1 = __uint_as_float(r[i + 1]);
-          float p0 = exp2f(v0 * c - mc), p1 = exp2f(v1 * c - mc);
-          if (diag) {
-            if ((cc * 32 + i) > row) p0 = 0.f;
-            if ((cc * 32 + i + 1) > row) p1 = 0.f;
-          }
-          sum += p0 + p1;
-          pk[cc * 16 + i / 2] = f2_to_bf2(p0, p1);
-        }
+      for (int i = 0; i < 128; i += 4) {
+        const float p0 = fast_exp2(fmaf(__uint_as_float(sr[i]), c, -mc));          // exp2(-inf) = 0 handles the mask
+        const float p1 = fast_exp2(fmaf(__uint_as_float(sr[i + 1]), c, -mc));
+        const float p2 = fast_exp2(fmaf(__uint_as_float(sr[i + 2]), c, -mc));
+        const float p3 = fast_exp2(fmaf(__uint_as_float(sr[i + 3]), c, -mc));
+        sum4[0] += p0; sum4[1] += p1; sum4[2] += p2; sum4[3] += p3;
+        pk[i / 2] = f2_to_bf2(p0, p1);
+        pk[i / 2 + 1] = f2_to_bf2(p2, p3);
       }
-      l = l * alpha + sum;
+      l = l * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
       m = mx;
       if (j > 0) {
         mbar_wait(o_done, (j - 1) & 1);          // PV_{j-1} retired: O is stable, the P buffer is free
         tc_fence_after_sync();
-        // rescale the running output
+        // rescale the running output - skipped when no row of this warp raised its maximum (the common case late in the row)
+        if (!__all_sync(0xffffffffu, alpha == 1.f)) {
 #pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(tO + lane_off + cc * 32, r);
-          tmem_ld_wait();
+          for (int cc = 0; cc < 2; ++cc) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tO + lane_off + cc * 32, r);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-          tmem_st_32x32b_x32(tO + lane_off + cc * 32, r);
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st_32x32b_x32(tO + lane_off + cc * 32, r);
+          }
+          tmem_st_wait();
         }
-        tmem_st_wait();
       }
       // P -> shared memory, K-major 128-byte-swizzled operand: chunk (keys/64), row r, 16-byte unit u at (u ^ (r & 7))
 #pragma unroll
