@@ -204,3 +204,13 @@ def test_wgrad_fp32_accumulate():
     ref = acc + a.float().t() @ b.float()
     G.mm_tn_acc(a, b, acc)
     assert rel(acc, ref) < 1e-3
+
+
+@pytest.mark.parametrize("B,S,Hq,Hkv", [(1, 128, 1, 1), (2, 256, 4, 2), (2, 1024, 4, 4), (3, 512, 8, 1)])
+def test_tcgen05_attention_forward(B, S, Hq, Hkv):
+    """Our tcgen05 causal attention forward (csrc/attn_sm100.cu) against the fp32 math reference."""
+    qkv = torch.randn(B * S, (Hq + 2 * Hkv) * 64, device=DEV).to(BF)
+    out, lse = A.tc_attention_fwd(qkv, B, S, Hq, Hkv)
+    ref, (lse_ref, _) = A.attention_fwd(qkv.float(), B, S, Hq, Hkv, 64)
+    assert rel(out, ref) < 5e-3
+    assert (lse - lse_ref).abs().max().item() < 1e-4
