@@ -22,7 +22,9 @@ namespace attn {
 constexpr int BQ = 128, BKV = 128, D = 64;
 constexpr int TILE_BYTES = 128 * 128;           // a [128 x 64] bf16 tile (128-byte rows)
 constexpr int THREADS = 192;
-constexpr int SMEM_BYTES = TILE_BYTES /*Q*/ + 2 * TILE_BYTES /*K*/ + 2 * TILE_BYTES /*V*/ + 2 * TILE_BYTES /*P*/ + 1024 + 256;
+// 7 tiles + barriers = 114,816 B: two CTAs per SM need 2 x (smem + 1 KB reserved) <= 227 KB, so there is no slack for a
+// manual 1024-byte round-up - the dynamic window is declared 1024-aligned instead (it starts at the CTA's smem base)
+constexpr int SMEM_BYTES = TILE_BYTES /*Q*/ + 2 * TILE_BYTES /*K*/ + 2 * TILE_BYTES /*V*/ + 2 * TILE_BYTES /*P*/ + 128;
 constexpr uint32_t TMEM_COLS = 256;             // S: [0,128)  O: [128,192)
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -39,8 +41,8 @@ struct Params {
 
 __global__ void __launch_bounds__(THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out, Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();     // swizzled tiles need 1024-byte alignment
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + TILE_BYTES;
   uint8_t* sV = sK + 2 * TILE_BYTES;
