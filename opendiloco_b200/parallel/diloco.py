@@ -21,6 +21,7 @@ Inner AdamW moments and the LR schedule are NOT reset at outer steps (SURVEY.md 
 from __future__ import annotations
 
 import contextlib
+import os
 import time
 from enum import Enum
 from typing import Callable, Iterable
@@ -641,6 +642,13 @@ class DiLoCoOptimizer:
             return None
         epoch, me = self.local_epoch, self.dht.rank_in_group
         key = lambda r: f"{self.run_id}/arrive/{epoch}/{r}"  # noqa: E731
+        inject = os.environ.get("ODB_FAULT_INJECT")      # "rank:epoch[:seconds]" - that worker arrives late (or never)
+        if inject:
+            f = inject.split(":")
+            if int(f[0]) == me and int(f[1]) == epoch:
+                delay = float(f[2]) if len(f) > 2 else 1e9
+                logger.warning(f"fault injection: worker {me} stalls {delay:.1f}s before outer step {epoch}")
+                time.sleep(min(delay, 3600.0))
         store.set(key(me), "1")
         budget = self.timeout_waiting_for_peers if self.all_reduce_strategy == AllReduceStrategy.WAIT_FOR_ALL \
             else self.matchmaking_time

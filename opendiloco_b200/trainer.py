@@ -25,6 +25,7 @@ from .optim.fused import FusedAdamW
 from .parallel import comm
 from .parallel.diloco import AllReduceStrategy, DiLoCoOptimizer
 from .parallel.swarm import DHT
+from .utils.profiling import StepTimer, nvtx_range
 from .utils.training import get_cosine_schedule_with_warmup
 
 
@@ -92,6 +93,7 @@ class DiLoCoTrainer:
         self.real_step = 0
         self.device = model.device
         self._loss_acc = torch.zeros((), dtype=torch.float32, device=self.device)
+        self.timer = StepTimer(enabled=False)        # trainer.timer.enabled = True to collect inner/outer CUDA-event timings
 
     # ------------------------------------------------------------------------------------------------
     @property
@@ -123,10 +125,14 @@ class DiLoCoTrainer:
         cfg = self.cfg
         self._loss_acc.zero_()
         scale = 1.0 / cfg.grad_accum
-        for _ in range(cfg.grad_accum):
-            loss = self.micro_step(next(batches), scale)
-            self._loss_acc.add_(loss, alpha=scale)
-        self.optimizer.step()          # clip + AdamW (+ outer step when due); gradients zeroed by the fused kernel
+        self.timer.start("inner_step")
+        with nvtx_range("micro_batches"):
+            for _ in range(cfg.grad_accum):
+                loss = self.micro_step(next(batches), scale)
+                self._loss_acc.add_(loss, alpha=scale)
+        with nvtx_range("optimizer_step"):
+            self.optimizer.step()      # clip + AdamW (+ outer step when due); gradients zeroed by the fused kernel
+        self.timer.stop("inner_step")
         self.scheduler.step()
         self.real_step += 1
         return self._loss_acc
