@@ -4,11 +4,12 @@
 // through ONE tensor map, writes out[T, Hq*64] token-major (the o-proj GEMM's A operand) and lse[B, Hq, S].
 //
 // One CTA per (batch, q-head, 128-query block); two CTAs co-reside per SM (112 KB smem, 256 TMEM columns each) so one
-// CTA's softmax overlaps the other's MMAs.  192 threads:
+// CTA's softmax overlaps the other's MMAs.  320 threads:
 //   warp 0     TMA: Q once, then K_j / V_j 128-key tiles through a 2-stage mbarrier ring
 //   warp 1     MMA: S = Q K_j^T  (tcgen05.mma M128 N128 K16 x4, both operands K-major, accumulator S in TMEM)
 //                   O += P V_j   (M128 N64 K16 x8; A = P from shared memory K-major, B = V_j tile MN-major)
-//   warps 2-5  softmax: one query row per thread (TMEM lane == row): tcgen05.ld S, online max/sum with exp2, causal mask
+//   warps 2-9  softmax: TWO threads per query row (TMEM lane == row; warps 2-5 take keys 0-63 of the tile, warps 6-9 keys
+//              64-127, row max exchanged through shared memory): tcgen05.ld S, online max/sum with exp2, causal mask
 //              on the diagonal tile, rescale O in TMEM (tcgen05.ld/st), write P (bf16) into the swizzled smem operand;
 //              epilogue: O / l -> bf16 -> swizzled staging tile -> TMA store
 #include "common.cuh"
@@ -21,10 +22,13 @@ namespace attn {
 
 constexpr int BQ = 128, BKV = 128, D = 64;
 constexpr int TILE_BYTES = 128 * 128;           // a [128 x 64] bf16 tile (128-byte rows)
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;
+constexpr int SOFTMAX_THREADS = 256;
 // 7 tiles + barriers = 114,816 B: two CTAs per SM need 2 x (smem + 1 KB reserved) <= 227 KB, so there is no slack for a
 // manual 1024-byte round-up - the dynamic window is declared 1024-aligned instead (it starts at the CTA's smem base)
-constexpr int SMEM_BYTES = TILE_BYTES /*Q*/ + 2 * TILE_BYTES /*K*/ + 2 * TILE_BYTES /*V*/ + 2 * TILE_BYTES /*P*/ + 128;
+constexpr int SMEM_BYTES = TILE_BYTES /*Q*/ + 2 * TILE_BYTES /*K x2*/ + TILE_BYTES /*V x1*/ + 2 * TILE_BYTES /*P*/ + 128 /*barriers*/;   // 98.4 KB + 2 KB static
+// the row-max / row-sum exchange between the two column halves lives in the (otherwise unused) tail of the barrier block
+// plus a small static array
 constexpr uint32_t TMEM_COLS = 256;             // S: [0,128)  O: [128,192)
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -42,15 +46,18 @@ struct Params {
 __global__ void __launch_bounds__(THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out, Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ float red[2 * 256];                 // row max / row sum exchange between the two column halves (double-buffered)
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();     // swizzled tiles need 1024-byte alignment
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + TILE_BYTES;
-  uint8_t* sV = sK + 2 * TILE_BYTES;
-  uint8_t* sP = sV + 2 * TILE_BYTES;            // two 64-key chunks of [128 rows x 128 B]
+  uint8_t* sV = sK + 2 * TILE_BYTES;            // single V stage: V_{j+1} is only needed after softmax_{j+1}
+  uint8_t* sP = sV + TILE_BYTES;                // two 64-key chunks of [128 rows x 128 B]
   uint64_t* q_full = reinterpret_cast<uint64_t*>(sP + 2 * TILE_BYTES);
-  uint64_t* kv_full = q_full + 1;               // [2]
-  uint64_t* kv_empty = kv_full + 2;             // [2]
-  uint64_t* s_full = kv_empty + 2;
+  uint64_t* k_full = q_full + 1;                // [2]
+  uint64_t* k_empty = k_full + 2;               // [2]
+  uint64_t* v_full = k_empty + 2;
+  uint64_t* v_empty = v_full + 1;
+  uint64_t* s_full = v_empty + 1;
   uint64_t* p_full = s_full + 1;
   uint64_t* o_done = p_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
@@ -68,9 +75,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     tma_prefetch_desc(&tmap_qkv);
     tma_prefetch_desc(&tmap_out);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 1);
     mbar_init(s_full, 1);
-    mbar_init(p_full, 4);      // one arrival per softmax warp
+    mbar_init(p_full, 8);      // one arrival per softmax warp
     mbar_init(o_done, 1);
     fence_barrier_init();
   }
@@ -87,10 +96,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       tma_load_2d(sQ, &tmap_qkv, q_full, col_q, row0);
       for (int j = 0; j < nkv; ++j) {
         const int st = j & 1;
-        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&kv_full[st], 2 * TILE_BYTES);
-        tma_load_2d(sK + st * TILE_BYTES, &tmap_qkv, &kv_full[st], col_k, b * p.S + j * BKV);
-        tma_load_2d(sV + st * TILE_BYTES, &tmap_qkv, &kv_full[st], col_v, b * p.S + j * BKV);
+        mbar_wait(&k_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
+        tma_load_2d(sK + st * TILE_BYTES, &tmap_qkv, &k_full[st], col_k, b * p.S + j * BKV);
+        mbar_wait(v_empty, (j & 1) ^ 1);
+        mbar_arrive_expect_tx(v_full, TILE_BYTES);
+        tma_load_2d(sV, &tmap_qkv, v_full, col_v, b * p.S + j * BKV);
       }
     }
   } else if (warp == 1) {
@@ -99,7 +110,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     mbar_wait(q_full, 0);
     for (int j = 0; j < nkv; ++j) {
       const int st = j & 1;
-      mbar_wait(&kv_full[st], (j >> 1) & 1);
+      mbar_wait(&k_full[st], (j >> 1) & 1);
       tc_fence_after_sync();
       if (elect_one()) {
         const uint64_t qd = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
@@ -107,18 +118,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) umma_ss(tS, qd + 2 * k, kd + 2 * k, idesc_qk, k > 0);
         umma_commit(s_full);
+        umma_commit(&k_empty[st]);               // K_j stage reusable once QK_j retired
       }
       __syncwarp();
       mbar_wait(p_full, j & 1);                  // P_j in smem, O rescaled, S_j consumed
+      mbar_wait(v_full, j & 1);
       tc_fence_after_sync();
       if (elect_one()) {
-        const uint64_t vd = make_smem_desc_sw128(smem_u32(sV + st * TILE_BYTES), 16, 1024);
+        const uint64_t vd = make_smem_desc_sw128(smem_u32(sV), 16, 1024);
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
           const uint64_t pd = make_smem_desc_sw128(smem_u32(sP + (k >> 2) * TILE_BYTES) + (k & 3) * 32, 16, 1024);
           umma_ss(tO, pd, vd + 128 * k, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
         }
-        umma_commit(&kv_empty[st]);              // K_j / V_j stage reusable
+        umma_commit(v_empty);                    // V stage reusable
         umma_commit(o_done);                     // O (and the P buffer) stable
       }
       __syncwarp();
@@ -127,40 +140,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     // ------------------------------------------------------------------ softmax / correction / epilogue
     const int q = warp & 3;
     const int row = q * 32 + lane;               // query row inside the tile == TMEM lane
+    const int half = (warp - 2) >> 2;            // 0: keys [0,64) of every tile and O columns [0,32) ; 1: the other halves
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    float m = -INFINITY, l = 0.f;
+    float m = -INFINITY, l = 0.f;                // l: this thread's half of the row sum
     const float c = p.scale_log2;
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after_sync();
       const bool diag = (j == qblk);
-      // the whole S row of this thread in one go: four TMEM loads in flight, a single wait
-      uint32_t sr[128];
-      tmem_ld_32x32b_x32(tS + lane_off + 0, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
-      tmem_ld_32x32b_x32(tS + lane_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
-      tmem_ld_32x32b_x32(tS + lane_off + 64, *reinterpret_cast<uint32_t(*)[32]>(&sr[64]));
-      tmem_ld_32x32b_x32(tS + lane_off + 96, *reinterpret_cast<uint32_t(*)[32]>(&sr[96]));
+      uint32_t sr[64];
+      tmem_ld_32x32b_x32(tS + lane_off + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
+      tmem_ld_32x32b_x32(tS + lane_off + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
       tmem_ld_wait();
       if (diag) {
 #pragma unroll
-        for (int i = 0; i < 128; ++i)
-          if (i > row) sr[i] = 0xff800000u;      // -inf
+        for (int i = 0; i < 64; ++i)
+          if (half * 64 + i > row) sr[i] = 0xff800000u;      // -inf
       }
-      float mx4[4] = {m, m, m, m};               // four independent chains instead of one 128-deep dependency
+      float mx4[4] = {m, m, m, m};
 #pragma unroll
-      for (int i = 0; i < 128; i += 4) {
+      for (int i = 0; i < 64; i += 4) {
         mx4[0] = fmaxf(mx4[0], __uint_as_float(sr[i]));
         mx4[1] = fmaxf(mx4[1], __uint_as_float(sr[i + 1]));
         mx4[2] = fmaxf(mx4[2], __uint_as_float(sr[i + 2]));
         mx4[3] = fmaxf(mx4[3], __uint_as_float(sr[i + 3]));
       }
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      // combine with the thread that owns the other 64 keys of this row
+      red[(j & 1) * 256 + half * 128 + row] = mx;
+      named_bar_sync(2, SOFTMAX_THREADS);
+      mx = fmaxf(mx, red[(j & 1) * 256 + (half ^ 1) * 128 + row]);
       const float alpha = fast_exp2((m - mx) * c);   // m = -inf on the first tile -> 0
       const float mc = mx * c;
-      uint32_t pk[64];
+      uint32_t pk[32];
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int i = 0; i < 128; i += 4) {
+      for (int i = 0; i < 64; i += 4) {
         const float p0 = fast_exp2(fmaf(__uint_as_float(sr[i]), c, -mc));          // exp2(-inf) = 0 handles the mask
         const float p1 = fast_exp2(fmaf(__uint_as_float(sr[i + 1]), c, -mc));
         const float p2 = fast_exp2(fmaf(__uint_as_float(sr[i + 2]), c, -mc));
@@ -174,24 +189,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       if (j > 0) {
         mbar_wait(o_done, (j - 1) & 1);          // PV_{j-1} retired: O is stable, the P buffer is free
         tc_fence_after_sync();
-        // rescale the running output - skipped when no row of this warp raised its maximum (the common case late in the row)
+        // rescale this thread's 32 columns of the running output - skipped when no row of the warp raised its maximum
         if (!__all_sync(0xffffffffu, alpha == 1.f)) {
-#pragma unroll 1
-          for (int cc = 0; cc < 2; ++cc) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tO + lane_off + cc * 32, r);
-            tmem_ld_wait();
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tO + lane_off + half * 32, r);
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-            tmem_st_32x32b_x32(tO + lane_off + cc * 32, r);
-          }
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+          tmem_st_32x32b_x32(tO + lane_off + half * 32, r);
           tmem_st_wait();
         }
       }
-      // P -> shared memory, K-major 128-byte-swizzled operand: chunk (keys/64), row r, 16-byte unit u at (u ^ (r & 7))
+      // P -> shared memory, K-major 128-byte-swizzled operand: chunk = half, row r, 16-byte unit u at (u ^ (r & 7))
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        uint8_t* dst = sP + (u >> 3) * TILE_BYTES + row * 128 + (((u & 7) ^ (row & 7)) * 16);
+      for (int u = 0; u < 8; ++u) {
+        uint8_t* dst = sP + half * TILE_BYTES + row * 128 + ((u ^ (row & 7)) * 16);
         *reinterpret_cast<uint4*>(dst) = make_uint4(pk[u * 4 + 0], pk[u * 4 + 1], pk[u * 4 + 2], pk[u * 4 + 3]);
       }
       fence_proxy_async_smem();
@@ -199,28 +211,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     }
-    // ---- epilogue
+    // ---- epilogue: total row sum = both halves
+    named_bar_sync(2, SOFTMAX_THREADS);          // everyone is done reading the last tile's max exchange
+    red[half * 128 + row] = l;
+    named_bar_sync(2, SOFTMAX_THREADS);
+    l += red[(half ^ 1) * 128 + row];
     mbar_wait(o_done, (nkv - 1) & 1);
     tc_fence_after_sync();
     const float inv_l = 1.f / l;
-    float o[64];
-#pragma unroll
-    for (int cc = 0; cc < 2; ++cc) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tO + lane_off + cc * 32, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o[cc * 32 + i] = __uint_as_float(r[i]) * inv_l;
-    }
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(tO + lane_off + half * 32, r);
+    tmem_ld_wait();
     uint8_t* stg = sP;                           // P buffer is free now: reuse its first chunk as the output staging tile
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const float f[8] = {o[u * 8 + 0], o[u * 8 + 1], o[u * 8 + 2], o[u * 8 + 3], o[u * 8 + 4], o[u * 8 + 5], o[u * 8 + 6], o[u * 8 + 7]};
-      *reinterpret_cast<uint4*>(stg + row * 128 + ((u ^ (row & 7)) * 16)) = pack8(f);
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[u * 8 + i]) * inv_l;
+      *reinterpret_cast<uint4*>(stg + row * 128 + (((half * 4 + u) ^ (row & 7)) * 16)) = pack8(f);
     }
-    p.lse[((size_t)b * p.Hq + h) * p.S + qblk * BQ + row] = (m * c + log2f(l)) * 0.6931471805599453f;
+    if (half == 0) p.lse[((size_t)b * p.Hq + h) * p.S + qblk * BQ + row] = (m * c + log2f(l)) * 0.6931471805599453f;
     fence_proxy_async_smem();
-    named_bar_sync(1, 128);
+    named_bar_sync(1, SOFTMAX_THREADS);
     if (threadIdx.x == 64) {
       tma_store_2d(&tmap_out, stg, col_q, row0);
       tma_store_commit();
