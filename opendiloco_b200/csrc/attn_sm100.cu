@@ -37,11 +37,29 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// 2^x for x <= 0 on the FMA/ALU pipes (Cody-Waite split + degree-3 polynomial, rel. error 6e-4 - far below the bf16
+// rounding of P).  Half of the exponentials go through this path so the 16-lane MUFU and the FMA pipe work in parallel
+// (the softmax of a 128x128 tile needs 16384 exponentials = 1024 MUFU cycles per SM otherwise).
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -126.f);
+  const float magic = 12582912.f;                       // 1.5 * 2^23: adding it rounds x to the nearest integer
+  const float t = x + magic;
+  const float n = t - magic;
+  const float r = x - n;                                // [-0.5, 0.5]
+  float pl = fmaf(r, 0.0555041087f, 0.2402265070f);
+  pl = fmaf(r, pl, 0.6931471806f);
+  pl = fmaf(r, pl, 1.0f);
+  return __int_as_float(__float_as_int(pl) + (__float_as_int(t) - __float_as_int(magic)) * 8388608);
+}
+
 struct Params {
   int B, S, Hq, Hkv;
   float scale_log2;        // softmax_scale * log2(e)
   float* lse;              // [B, Hq, S], natural log
+  long long* dbg;          // optional timeline of CTA (0,0,0): [tile][16] clock64 stamps (nullptr = off)
 };
+
+#define ATT_STAMP(slot) do { if (dbg_on) p.dbg[j * 16 + (slot)] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out, Params p) {
@@ -108,33 +126,43 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);   // S[128,128] = Q (K-major) x K^T (K-major)
     constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, D, 0, 1);     // O[128,64] = P (K-major) x V (MN-major)
     mbar_wait(q_full, 0);
+    const bool leader = elect_one();             // the same lane issues every MMA / commit of this CTA
+    const uint64_t qd = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+    const uint64_t vd = make_smem_desc_sw128(smem_u32(sV), 16, 1024);
+    const uint64_t pd0 = make_smem_desc_sw128(smem_u32(sP), 16, 1024);
+    const uint64_t pd1 = make_smem_desc_sw128(smem_u32(sP + TILE_BYTES), 16, 1024);
+    const uint64_t kd0 = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+    const uint64_t kd1 = make_smem_desc_sw128(smem_u32(sK + TILE_BYTES), 16, 1024);
+    const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
     for (int j = 0; j < nkv; ++j) {
       const int st = j & 1;
       mbar_wait(&k_full[st], (j >> 1) & 1);
+      ATT_STAMP(8);
       tc_fence_after_sync();
-      if (elect_one()) {
-        const uint64_t qd = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
-        const uint64_t kd = make_smem_desc_sw128(smem_u32(sK + st * TILE_BYTES), 16, 1024);
-#pragma unroll
-        for (int k = 0; k < D / 16; ++k) umma_ss(tS, qd + 2 * k, kd + 2 * k, idesc_qk, k > 0);
+      if (leader) {
+        const uint64_t kd = st ? kd1 : kd0;
+        umma_ss(tS, qd, kd, idesc_qk, 0u);
+        umma_ss(tS, qd + 2, kd + 2, idesc_qk, 1u);
+        umma_ss(tS, qd + 4, kd + 4, idesc_qk, 1u);
+        umma_ss(tS, qd + 6, kd + 6, idesc_qk, 1u);
         umma_commit(s_full);
         umma_commit(&k_empty[st]);               // K_j stage reusable once QK_j retired
       }
       __syncwarp();
+      ATT_STAMP(9);
       mbar_wait(p_full, j & 1);                  // P_j in smem, O rescaled, S_j consumed
+      ATT_STAMP(10);
       mbar_wait(v_full, j & 1);
       tc_fence_after_sync();
-      if (elect_one()) {
-        const uint64_t vd = make_smem_desc_sw128(smem_u32(sV), 16, 1024);
+      if (leader) {
+        umma_ss(tO, pd0, vd, idesc_pv, j > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k) {
-          const uint64_t pd = make_smem_desc_sw128(smem_u32(sP + (k >> 2) * TILE_BYTES) + (k & 3) * 32, 16, 1024);
-          umma_ss(tO, pd, vd + 128 * k, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-        }
+        for (int k = 1; k < BKV / 16; ++k) umma_ss(tO, ((k >> 2) ? pd1 : pd0) + 2 * (k & 3), vd + 128 * k, idesc_pv, 1u);
         umma_commit(v_empty);                    // V stage reusable
         umma_commit(o_done);                     // O (and the P buffer) stable
       }
       __syncwarp();
+      ATT_STAMP(11);
     }
   } else {
     // ------------------------------------------------------------------ softmax / correction / epilogue
@@ -144,14 +172,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     float m = -INFINITY, l = 0.f;                // l: this thread's half of the row sum
     const float c = p.scale_log2;
+    const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 64;
     for (int j = 0; j < nkv; ++j) {
+      ATT_STAMP(0);
       mbar_wait(s_full, j & 1);
       tc_fence_after_sync();
+      ATT_STAMP(1);
       const bool diag = (j == qblk);
       uint32_t sr[64];
       tmem_ld_32x32b_x32(tS + lane_off + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
       tmem_ld_32x32b_x32(tS + lane_off + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
       tmem_ld_wait();
+      ATT_STAMP(2);
       if (diag) {
 #pragma unroll
         for (int i = 0; i < 64; ++i)
@@ -169,7 +201,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       // combine with the thread that owns the other 64 keys of this row
       red[(j & 1) * 256 + half * 128 + row] = mx;
       named_bar_sync(2, SOFTMAX_THREADS);
+      ATT_STAMP(3);
       mx = fmaxf(mx, red[(j & 1) * 256 + (half ^ 1) * 128 + row]);
+      // lazy rescaling: the reference point m only moves when the row maximum grew by more than 8 in the exp2 domain;
+      // until then probabilities may exceed 1 (<= 2^8), which fp32 sums and bf16 P represent without trouble, and O / l
+      // need no correction.  Both threads of a row see the same mx, so they take the same decision.
+      if ((mx - m) * c <= 8.f) mx = m;
       const float alpha = fast_exp2((m - mx) * c);   // m = -inf on the first tile -> 0
       const float mc = mx * c;
       uint32_t pk[32];
@@ -177,15 +214,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
 #pragma unroll
       for (int i = 0; i < 64; i += 4) {
         const float p0 = fast_exp2(fmaf(__uint_as_float(sr[i]), c, -mc));          // exp2(-inf) = 0 handles the mask
-        const float p1 = fast_exp2(fmaf(__uint_as_float(sr[i + 1]), c, -mc));
+        const float p1 = poly_exp2(fmaf(__uint_as_float(sr[i + 1]), c, -mc));     // FMA-pipe version (clamps -inf)
         const float p2 = fast_exp2(fmaf(__uint_as_float(sr[i + 2]), c, -mc));
-        const float p3 = fast_exp2(fmaf(__uint_as_float(sr[i + 3]), c, -mc));
+        const float p3 = poly_exp2(fmaf(__uint_as_float(sr[i + 3]), c, -mc));
         sum4[0] += p0; sum4[1] += p1; sum4[2] += p2; sum4[3] += p3;
         pk[i / 2] = f2_to_bf2(p0, p1);
         pk[i / 2 + 1] = f2_to_bf2(p2, p3);
       }
       l = l * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
       m = mx;
+      ATT_STAMP(4);
       if (j > 0) {
         mbar_wait(o_done, (j - 1) & 1);          // PV_{j-1} retired: O is stable, the P buffer is free
         tc_fence_after_sync();
@@ -200,6 +238,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
           tmem_st_wait();
         }
       }
+      ATT_STAMP(5);
       // P -> shared memory, K-major 128-byte-swizzled operand: chunk = half, row r, 16-byte unit u at (u ^ (r & 7))
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
@@ -207,9 +246,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         *reinterpret_cast<uint4*>(dst) = make_uint4(pk[u * 4 + 0], pk[u * 4 + 1], pk[u * 4 + 2], pk[u * 4 + 3]);
       }
       fence_proxy_async_smem();
+      ATT_STAMP(6);
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      ATT_STAMP(7);
     }
     // ---- epilogue: total row sum = both halves
     named_bar_sync(2, SOFTMAX_THREADS);          // everyone is done reading the last tile's max exchange
@@ -249,7 +290,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
 
 // qkv: [B*S, (Hq+2*Hkv)*64] bf16 (row stride ld_qkv elements); out: [B*S, Hq*64] bf16; lse: [B, Hq, S] fp32
 ODB_EXPORT int odb_attn_fwd(const void* qkv, void* out, void* lse, int B, int S, int Hq, int Hkv, long long ld_qkv,
-                            long long ld_out, float softmax_scale, cudaStream_t st) {
+                            long long ld_out, float softmax_scale, void* dbg, cudaStream_t st) {
   using namespace attn;
   if (S % BQ || Hq % Hkv || ld_qkv % 8 || ld_out % 8) return -1;
   CUtensorMap tq, to;
@@ -261,6 +302,7 @@ ODB_EXPORT int odb_attn_fwd(const void* qkv, void* out, void* lse, int B, int S,
   p.B = B; p.S = S; p.Hq = Hq; p.Hkv = Hkv;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   p.lse = (float*)lse;
+  p.dbg = (long long*)dbg;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);

@@ -26,16 +26,17 @@ _FLASH = None
 _LIB = os.environ.get("ODB_ATTN_LIB", "cudnn")
 _TC_FWD = os.environ.get("ODB_TC_ATTN", "0") == "1"      # our tcgen05 forward kernel (csrc/attn_sm100.cu)
 _lib.register_optional("odb_attn_fwd", [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                        ctypes.c_int, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p])
+                                        ctypes.c_int, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p])
 
 
-def tc_attention_fwd(qkv: torch.Tensor, B: int, S: int, Hq: int, Hkv: int, D: int = 64):
+def tc_attention_fwd(qkv: torch.Tensor, B: int, S: int, Hq: int, Hkv: int, D: int = 64, dbg: torch.Tensor | None = None):
     """Our tcgen05 causal attention forward.  Returns (out [T, Hq*D] bf16, lse [B, Hq, S] fp32, natural log)."""
     assert D == 64 and S % 128 == 0 and qkv.dtype == torch.bfloat16 and qkv.stride(1) == 1
     out = torch.empty(B * S, Hq * D, dtype=qkv.dtype, device=qkv.device)
     lse = torch.empty(B, Hq, S, dtype=torch.float32, device=qkv.device)
     _lib.check(_lib.cuda_lib().odb_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, S, Hq, Hkv, qkv.stride(0),
-                                            out.stride(0), 1.0 / math.sqrt(D), _lib.stream_ptr(qkv)), "attn_fwd")
+                                            out.stride(0), 1.0 / math.sqrt(D), dbg.data_ptr() if dbg is not None else None,
+                                            _lib.stream_ptr(qkv)), "attn_fwd")
     _lib.count_launch()
     return out, lse
 
