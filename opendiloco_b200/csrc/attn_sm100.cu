@@ -26,10 +26,10 @@ constexpr int THREADS = 320;
 constexpr int SOFTMAX_THREADS = 256;
 // 7 tiles + barriers = 114,816 B: two CTAs per SM need 2 x (smem + 1 KB reserved) <= 227 KB, so there is no slack for a
 // manual 1024-byte round-up - the dynamic window is declared 1024-aligned instead (it starts at the CTA's smem base)
-constexpr int SMEM_BYTES = TILE_BYTES /*Q*/ + 2 * TILE_BYTES /*K x2*/ + TILE_BYTES /*V x1*/ + 2 * TILE_BYTES /*P*/ + 128 /*barriers*/;   // 98.4 KB + 2 KB static
+constexpr int SMEM_BYTES = TILE_BYTES /*Q*/ + 2 * TILE_BYTES /*K x2*/ + TILE_BYTES /*V x1*/ + TILE_BYTES /*out staging*/ + 128 /*barriers*/;   // 82 KB + 2 KB static
 // the row-max / row-sum exchange between the two column halves lives in the (otherwise unused) tail of the barrier block
 // plus a small static array
-constexpr uint32_t TMEM_COLS = 256;             // S: [0,128)  O: [128,192)
+constexpr uint32_t TMEM_COLS = 256;             // S: [0,128)  O: [128,192)  P (bf16, 2 keys per column): [192,256)
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -52,6 +52,58 @@ __device__ __forceinline__ float poly_exp2(float x) {
   return __int_as_float(__float_as_int(pl) + (__float_as_int(t) - __float_as_int(magic)) * 8388608);
 }
 
+// ---- packed fp32x2 helpers (Blackwell FFMA2 / FADD2): one instruction, two lanes of a 64-bit register pair
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t pack2u(uint32_t a, uint32_t b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t cvt_bf16x2(uint64_t v) {
+  float a, b;
+  unpack2(v, a, b);
+  return f2_to_bf2(a, b);
+}
+// 2^y for two values y <= ~8 on the FMA / ALU pipes: n = round(y), r = y - n in [-0.5, 0.5], 2^r by a degree-3 polynomial
+// (rel. error 6e-4, far below the bf16 rounding of P), then n is added to the exponent field.
+__device__ __forceinline__ uint64_t poly_exp2x2(uint64_t y) {
+  float y0, y1;
+  unpack2(y, y0, y1);
+  y = pack2(fmaxf(y0, -126.f), fmaxf(y1, -126.f));
+  const float magic = 12582912.f;                               // 1.5 * 2^23
+  const uint64_t mg = pack2(magic, magic), nmg = pack2(-magic, -magic);
+  const uint64_t t = fadd2(y, mg);
+  const uint64_t n = fadd2(t, nmg);
+  float n0, n1;
+  unpack2(n, n0, n1);
+  const uint64_t r = fadd2(y, pack2(-n0, -n1));
+  uint64_t pl = ffma2(r, pack2(0.0555041087f, 0.0555041087f), pack2(0.2402265070f, 0.2402265070f));
+  pl = ffma2(r, pl, pack2(0.6931471806f, 0.6931471806f));
+  pl = ffma2(r, pl, pack2(1.0f, 1.0f));
+  float p0, p1, t0, t1;
+  unpack2(pl, p0, p1);
+  unpack2(t, t0, t1);
+  const int mi = __float_as_int(magic);
+  p0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) - mi) * 8388608);
+  p1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) - mi) * 8388608);
+  return pack2(p0, p1);
+}
+
 struct Params {
   int B, S, Hq, Hkv;
   float scale_log2;        // softmax_scale * log2(e)
@@ -69,8 +121,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + TILE_BYTES;
   uint8_t* sV = sK + 2 * TILE_BYTES;            // single V stage: V_{j+1} is only needed after softmax_{j+1}
-  uint8_t* sP = sV + TILE_BYTES;                // two 64-key chunks of [128 rows x 128 B]
-  uint64_t* q_full = reinterpret_cast<uint64_t*>(sP + 2 * TILE_BYTES);
+  uint8_t* sOut = sV + TILE_BYTES;              // output staging tile (P lives in tensor memory)
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(sOut + TILE_BYTES);
   uint64_t* k_full = q_full + 1;                // [2]
   uint64_t* k_empty = k_full + 2;               // [2]
   uint64_t* v_full = k_empty + 2;
@@ -106,7 +158,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  const uint32_t tS = tmem_base, tO = tmem_base + 128, tP = tmem_base + 192;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -124,13 +176,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);   // S[128,128] = Q (K-major) x K^T (K-major)
-    constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, D, 0, 1);     // O[128,64] = P (K-major) x V (MN-major)
+    constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, D, 0, 1);     // O[128,64] = P (TMEM, K-major) x V (smem, MN-major)
     mbar_wait(q_full, 0);
     const bool leader = elect_one();             // the same lane issues every MMA / commit of this CTA
     const uint64_t qd = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
     const uint64_t vd = make_smem_desc_sw128(smem_u32(sV), 16, 1024);
-    const uint64_t pd0 = make_smem_desc_sw128(smem_u32(sP), 16, 1024);
-    const uint64_t pd1 = make_smem_desc_sw128(smem_u32(sP + TILE_BYTES), 16, 1024);
     const uint64_t kd0 = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
     const uint64_t kd1 = make_smem_desc_sw128(smem_u32(sK + TILE_BYTES), 16, 1024);
     const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
@@ -155,9 +205,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       mbar_wait(v_full, j & 1);
       tc_fence_after_sync();
       if (leader) {
-        umma_ss(tO, pd0, vd, idesc_pv, j > 0 ? 1u : 0u);
+        // A operand straight from tensor memory: 16 keys of P = 8 columns per K step, no shared-memory read for A
+        umma_ts(tO, tP, vd, idesc_pv, j > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 1; k < BKV / 16; ++k) umma_ss(tO, ((k >> 2) ? pd1 : pd0) + 2 * (k & 3), vd + 128 * k, idesc_pv, 1u);
+        for (int k = 1; k < BKV / 16; ++k) umma_ts(tO, tP + 8 * k, vd + 128 * k, idesc_pv, 1u);
         umma_commit(v_empty);                    // V stage reusable
         umma_commit(o_done);                     // O (and the P buffer) stable
       }
@@ -209,25 +260,37 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       if ((mx - m) * c <= 8.f) mx = m;
       const float alpha = fast_exp2((m - mx) * c);   // m = -inf on the first tile -> 0
       const float mc = mx * c;
+      // p = exp2(s*c - m*c) with packed fp32x2 arithmetic (FFMA2 / FADD2).  Of every four elements two go through the
+      // MUFU (ex2.approx) and two through a Cody-Waite + degree-3 polynomial on the FMA pipe, so both pipes work in
+      // parallel (16384 exponentials per tile would otherwise keep the 16-lane MUFU busy for 1024 cycles per SM).
       uint32_t pk[32];
-      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint64_t c2 = pack2(c, c), nmc2 = pack2(-mc, -mc);
+      uint64_t sum2a = pack2(0.f, 0.f), sum2b = pack2(0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < 64; i += 4) {
-        const float p0 = fast_exp2(fmaf(__uint_as_float(sr[i]), c, -mc));          // exp2(-inf) = 0 handles the mask
-        const float p1 = poly_exp2(fmaf(__uint_as_float(sr[i + 1]), c, -mc));     // FMA-pipe version (clamps -inf)
-        const float p2 = fast_exp2(fmaf(__uint_as_float(sr[i + 2]), c, -mc));
-        const float p3 = poly_exp2(fmaf(__uint_as_float(sr[i + 3]), c, -mc));
-        sum4[0] += p0; sum4[1] += p1; sum4[2] += p2; sum4[3] += p3;
-        pk[i / 2] = f2_to_bf2(p0, p1);
-        pk[i / 2 + 1] = f2_to_bf2(p2, p3);
+        const uint64_t ya = ffma2(pack2u(sr[i], sr[i + 1]), c2, nmc2);
+        const uint64_t yb = ffma2(pack2u(sr[i + 2], sr[i + 3]), c2, nmc2);
+        float a0, a1;
+        unpack2(ya, a0, a1);
+        const uint64_t pa = pack2(fast_exp2(a0), fast_exp2(a1));      // MUFU pair (exp2(-inf) = 0 handles the mask)
+        const uint64_t pb = poly_exp2x2(yb);                          // FMA-pipe pair (clamped at 2^-126)
+        sum2a = fadd2(sum2a, pa);
+        sum2b = fadd2(sum2b, pb);
+        pk[i / 2] = cvt_bf16x2(pa);
+        pk[i / 2 + 1] = cvt_bf16x2(pb);
       }
-      l = l * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
+      {
+        float s0, s1, s2, s3;
+        unpack2(sum2a, s0, s1);
+        unpack2(sum2b, s2, s3);
+        l = l * alpha + ((s0 + s1) + (s2 + s3));
+      }
       m = mx;
       ATT_STAMP(4);
       if (j > 0) {
-        mbar_wait(o_done, (j - 1) & 1);          // PV_{j-1} retired: O is stable, the P buffer is free
+        mbar_wait(o_done, (j - 1) & 1);          // PV_{j-1} retired: O is stable, P may be overwritten
         tc_fence_after_sync();
-        // rescale this thread's 32 columns of the running output - skipped when no row of the warp raised its maximum
+        // rescale this thread's 32 columns of the running output - skipped when no row of the warp moved its reference max
         if (!__all_sync(0xffffffffu, alpha == 1.f)) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(tO + lane_off + half * 32, r);
@@ -235,17 +298,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
 #pragma unroll
           for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
           tmem_st_32x32b_x32(tO + lane_off + half * 32, r);
-          tmem_st_wait();
         }
       }
       ATT_STAMP(5);
-      // P -> shared memory, K-major 128-byte-swizzled operand: chunk = half, row r, 16-byte unit u at (u ^ (r & 7))
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        uint8_t* dst = sP + half * TILE_BYTES + row * 128 + ((u ^ (row & 7)) * 16);
-        *reinterpret_cast<uint4*>(dst) = make_uint4(pk[u * 4 + 0], pk[u * 4 + 1], pk[u * 4 + 2], pk[u * 4 + 3]);
-      }
-      fence_proxy_async_smem();
+      // P -> tensor memory: row == lane, this thread's 64 keys = 32 packed columns (the MMA reads A from TMEM)
+      tmem_st_32x32b_x32(tP + lane_off + half * 32, pk);
+      tmem_st_wait();
       ATT_STAMP(6);
       tc_fence_before_sync();
       __syncwarp();
@@ -263,7 +321,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     uint32_t r[32];
     tmem_ld_32x32b_x32(tO + lane_off + half * 32, r);
     tmem_ld_wait();
-    uint8_t* stg = sP;                           // P buffer is free now: reuse its first chunk as the output staging tile
+    uint8_t* stg = sOut;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       float f[8];
