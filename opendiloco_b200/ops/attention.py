@@ -29,6 +29,27 @@ _lib.register_optional("odb_attn_fwd", [ctypes.c_void_p, ctypes.c_void_p, ctypes
                                         ctypes.c_int, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p])
 
 
+_lib.register_optional("odb_attn_bwd", [ctypes.c_void_p] * 8 + [ctypes.c_int] * 4 + [ctypes.c_longlong, ctypes.c_longlong, ctypes.c_float,
+                                                                                   ctypes.c_void_p])
+
+
+def tc_attention_bwd(dout: torch.Tensor, qkv: torch.Tensor, out: torch.Tensor, lse: torch.Tensor, B: int, S: int, Hq: int, Hkv: int,
+                     D: int = 64):
+    """Our tcgen05 attention backward.  Returns (dq [T,Hq*D] bf16, dk [T,Hkv*D] bf16, dv [T,Hkv*D] bf16)."""
+    assert D == 64 and S % 128 == 0 and dout.is_contiguous() and out.is_contiguous()
+    T = B * S
+    dev = qkv.device
+    dq_acc = torch.zeros(T, Hq * D, dtype=torch.float32, device=dev)       # accumulated across key tiles by TMA reduce-add
+    dk = torch.empty(T, Hkv * D, dtype=qkv.dtype, device=dev)
+    dv = torch.empty(T, Hkv * D, dtype=qkv.dtype, device=dev)
+    dsum = torch.empty(B, Hq, S, dtype=torch.float32, device=dev)
+    _lib.check(_lib.cuda_lib().odb_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dsum.data_ptr(),
+                                            dq_acc.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, S, Hq, Hkv, qkv.stride(0),
+                                            out.stride(0), 1.0 / math.sqrt(D), _lib.stream_ptr(qkv)), "attn_bwd")
+    _lib.count_launch(2)
+    return dq_acc.to(qkv.dtype), dk, dv
+
+
 def tc_attention_fwd(qkv: torch.Tensor, B: int, S: int, Hq: int, Hkv: int, D: int = 64, dbg: torch.Tensor | None = None):
     """Our tcgen05 causal attention forward.  Returns (out [T, Hq*D] bf16, lse [B, Hq, S] fp32, natural log)."""
     assert D == 64 and S % 128 == 0 and qkv.dtype == torch.bfloat16 and qkv.stride(1) == 1
