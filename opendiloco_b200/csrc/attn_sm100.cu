@@ -129,7 +129,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   uint64_t* v_empty = v_full + 1;
   uint64_t* s_full = v_empty + 1;
   uint64_t* p_full = s_full + 1;
-  uint64_t* o_done = p_full + 1;
+  uint64_t* s_free = p_full + 1;                // S_j is in registers: the next QK may overwrite the S columns
+  uint64_t* o_done = s_free + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -150,6 +151,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     mbar_init(v_empty, 1);
     mbar_init(s_full, 1);
     mbar_init(p_full, 8);      // one arrival per softmax warp
+    mbar_init(s_free, 8);
     mbar_init(o_done, 1);
     fence_barrier_init();
   }
@@ -184,23 +186,40 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     const uint64_t kd0 = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
     const uint64_t kd1 = make_smem_desc_sw128(smem_u32(sK + TILE_BYTES), 16, 1024);
     const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+    // S_0 = Q K_0^T
+    mbar_wait(&k_full[0], 0);
+    tc_fence_after_sync();
+    if (leader) {
+      umma_ss(tS, qd, kd0, idesc_qk, 0u);
+      umma_ss(tS, qd + 2, kd0 + 2, idesc_qk, 1u);
+      umma_ss(tS, qd + 4, kd0 + 4, idesc_qk, 1u);
+      umma_ss(tS, qd + 6, kd0 + 6, idesc_qk, 1u);
+      umma_commit(s_full);
+      umma_commit(&k_empty[0]);
+    }
+    __syncwarp();
     for (int j = 0; j < nkv; ++j) {
-      const int st = j & 1;
-      mbar_wait(&k_full[st], (j >> 1) & 1);
       ATT_STAMP(8);
-      tc_fence_after_sync();
-      if (leader) {
-        const uint64_t kd = st ? kd1 : kd0;
-        umma_ss(tS, qd, kd, idesc_qk, 0u);
-        umma_ss(tS, qd + 2, kd + 2, idesc_qk, 1u);
-        umma_ss(tS, qd + 4, kd + 4, idesc_qk, 1u);
-        umma_ss(tS, qd + 6, kd + 6, idesc_qk, 1u);
-        umma_commit(s_full);
-        umma_commit(&k_empty[st]);               // K_j stage reusable once QK_j retired
+      // As soon as the softmax warps hold S_j in registers, the next QK^T goes into the same TMEM columns - it runs while
+      // they compute the probabilities, so S_{j+1} is waiting for them when they come back.
+      if (j + 1 < nkv) {
+        const int st = (j + 1) & 1;
+        mbar_wait(s_free, j & 1);
+        mbar_wait(&k_full[st], ((j + 1) >> 1) & 1);
+        tc_fence_after_sync();
+        if (leader) {
+          const uint64_t kd = st ? kd1 : kd0;
+          umma_ss(tS, qd, kd, idesc_qk, 0u);
+          umma_ss(tS, qd + 2, kd + 2, idesc_qk, 1u);
+          umma_ss(tS, qd + 4, kd + 4, idesc_qk, 1u);
+          umma_ss(tS, qd + 6, kd + 6, idesc_qk, 1u);
+          umma_commit(s_full);
+          umma_commit(&k_empty[st]);             // K stage reusable once this QK retired
+        }
+        __syncwarp();
       }
-      __syncwarp();
       ATT_STAMP(9);
-      mbar_wait(p_full, j & 1);                  // P_j in smem, O rescaled, S_j consumed
+      mbar_wait(p_full, j & 1);                  // P_j in tensor memory, O rescaled
       ATT_STAMP(10);
       mbar_wait(v_full, j & 1);
       tc_fence_after_sync();
@@ -210,7 +229,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
 #pragma unroll
         for (int k = 1; k < BKV / 16; ++k) umma_ts(tO, tP + 8 * k, vd + 128 * k, idesc_pv, 1u);
         umma_commit(v_empty);                    // V stage reusable
-        umma_commit(o_done);                     // O (and the P buffer) stable
+        umma_commit(o_done);                     // O (and P) stable
       }
       __syncwarp();
       ATT_STAMP(11);
@@ -234,6 +253,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       tmem_ld_32x32b_x32(tS + lane_off + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
       tmem_ld_32x32b_x32(tS + lane_off + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
       tmem_ld_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);        // S_j now lives in registers
       ATT_STAMP(2);
       if (diag) {
 #pragma unroll
