@@ -166,11 +166,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     if (lane == 0) {
       mbar_arrive_expect_tx(q_full, TILE_BYTES);
       tma_load_2d(sQ, &tmap_qkv, q_full, col_q, row0);
-      for (int j = 0; j < nkv; ++j) {
+      // K runs one tile ahead of V: K_{j+1} is requested as soon as its stage is free (QK_{j-1} retired), V_j after
+      // PV_{j-1} retired - V_j is not needed before softmax_j is done, K_{j+1} is needed right after softmax_j's S load.
+      auto load_k = [&](int j) {
         const int st = j & 1;
         mbar_wait(&k_empty[st], ((j >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
         tma_load_2d(sK + st * TILE_BYTES, &tmap_qkv, &k_full[st], col_k, b * p.S + j * BKV);
+      };
+      load_k(0);
+      for (int j = 0; j < nkv; ++j) {
+        if (j + 1 < nkv) load_k(j + 1);
         mbar_wait(v_empty, (j & 1) ^ 1);
         mbar_arrive_expect_tx(v_full, TILE_BYTES);
         tma_load_2d(sV, &tmap_qkv, v_full, col_v, b * p.S + j * BKV);
