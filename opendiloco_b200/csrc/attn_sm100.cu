@@ -14,9 +14,11 @@
 //              epilogue: O / l -> bf16 -> swizzled staging tile -> TMA store
 #include "common.cuh"
 #include "sm100_ptx.cuh"
+#include "attn_math.cuh"
 
 using namespace odb;
 using namespace sm100;
+using namespace attn_math;
 
 namespace attn {
 
@@ -30,79 +32,6 @@ constexpr int SMEM_BYTES = TILE_BYTES /*Q*/ + 2 * TILE_BYTES /*K x2*/ + TILE_BYT
 // the row-max / row-sum exchange between the two column halves lives in the (otherwise unused) tail of the barrier block
 // plus a small static array
 constexpr uint32_t TMEM_COLS = 256;             // S: [0,128)  O: [128,192)  P (bf16, 2 keys per column): [192,256)
-
-__device__ __forceinline__ float fast_exp2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// 2^x for x <= 0 on the FMA/ALU pipes (Cody-Waite split + degree-3 polynomial, rel. error 6e-4 - far below the bf16
-// rounding of P).  Half of the exponentials go through this path so the 16-lane MUFU and the FMA pipe work in parallel
-// (the softmax of a 128x128 tile needs 16384 exponentials = 1024 MUFU cycles per SM otherwise).
-__device__ __forceinline__ float poly_exp2(float x) {
-  x = fmaxf(x, -126.f);
-  const float magic = 12582912.f;                       // 1.5 * 2^23: adding it rounds x to the nearest integer
-  const float t = x + magic;
-  const float n = t - magic;
-  const float r = x - n;                                // [-0.5, 0.5]
-  float pl = fmaf(r, 0.0555041087f, 0.2402265070f);
-  pl = fmaf(r, pl, 0.6931471806f);
-  pl = fmaf(r, pl, 1.0f);
-  return __int_as_float(__float_as_int(pl) + (__float_as_int(t) - __float_as_int(magic)) * 8388608);
-}
-
-// ---- packed fp32x2 helpers (Blackwell FFMA2 / FADD2): one instruction, two lanes of a 64-bit register pair
-__device__ __forceinline__ uint64_t pack2(float a, float b) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ uint64_t pack2u(uint32_t a, uint32_t b) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b));
-  return r;
-}
-__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ uint32_t cvt_bf16x2(uint64_t v) {
-  float a, b;
-  unpack2(v, a, b);
-  return f2_to_bf2(a, b);
-}
-// 2^y for two values y <= ~8 on the FMA / ALU pipes: n = round(y), r = y - n in [-0.5, 0.5], 2^r by a degree-3 polynomial
-// (rel. error 6e-4, far below the bf16 rounding of P), then n is added to the exponent field.
-__device__ __forceinline__ uint64_t poly_exp2x2(uint64_t y) {
-  float y0, y1;
-  unpack2(y, y0, y1);
-  y = pack2(fmaxf(y0, -126.f), fmaxf(y1, -126.f));
-  const float magic = 12582912.f;                               // 1.5 * 2^23
-  const uint64_t mg = pack2(magic, magic), nmg = pack2(-magic, -magic);
-  const uint64_t t = fadd2(y, mg);
-  const uint64_t n = fadd2(t, nmg);
-  float n0, n1;
-  unpack2(n, n0, n1);
-  const uint64_t r = fadd2(y, pack2(-n0, -n1));
-  uint64_t pl = ffma2(r, pack2(0.0555041087f, 0.0555041087f), pack2(0.2402265070f, 0.2402265070f));
-  pl = ffma2(r, pl, pack2(0.6931471806f, 0.6931471806f));
-  pl = ffma2(r, pl, pack2(1.0f, 1.0f));
-  float p0, p1, t0, t1;
-  unpack2(pl, p0, p1);
-  unpack2(t, t0, t1);
-  const int mi = __float_as_int(magic);
-  p0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) - mi) * 8388608);
-  p1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) - mi) * 8388608);
-  return pack2(p0, p1);
-}
 
 struct Params {
   int B, S, Hq, Hkv;
@@ -131,15 +60,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   uint64_t* p_full = s_full + 1;
   uint64_t* s_free = p_full + 1;                // S_j is in registers: the next QK may overwrite the S columns
   uint64_t* o_done = s_free + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+  uint64_t* q_empty = o_done + 1;               // every QK^T of the current query tile retired: Q may be replaced
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nq = p.S / BQ;
-  const int qblk = nq - 1 - (int)blockIdx.x;    // longest (most KV tiles) first
+  // Each CTA owns TWO query tiles of one (batch, head): tile nq-1-x (long) and tile x (short).  Every CTA therefore
+  // walks nq+1 key tiles - a perfectly balanced grid - and the fixed cost (barrier init, TMEM allocation, pipeline
+  // fill) is paid once per ~nq+1 tiles instead of once per ~nq/2.  `tg` below is the CTA-wide running tile index that
+  // all barrier parities are derived from.
+  const int qb[2] = {nq - 1 - (int)blockIdx.x, (int)blockIdx.x};
+  const int nitems = qb[0] != qb[1] ? 2 : 1;
   const int h = blockIdx.y, b = blockIdx.z;
   const int hk = h / (p.Hq / p.Hkv);
-  const int nkv = qblk + 1;                     // causal: key tiles 0..qblk
-  const int row0 = b * p.S + qblk * BQ;         // first token row of this query tile
   const int col_q = h * D, col_k = (p.Hq + hk) * D, col_v = (p.Hq + p.Hkv + hk) * D;
 
   if (warp == 0 && lane == 0) {
@@ -153,6 +86,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     mbar_init(p_full, 8);      // one arrival per softmax warp
     mbar_init(s_free, 8);
     mbar_init(o_done, 1);
+    mbar_init(q_empty, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -164,70 +98,74 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, TILE_BYTES);
-      tma_load_2d(sQ, &tmap_qkv, q_full, col_q, row0);
       // K runs one tile ahead of V: K_{j+1} is requested as soon as its stage is free (QK_{j-1} retired), V_j after
       // PV_{j-1} retired - V_j is not needed before softmax_j is done, K_{j+1} is needed right after softmax_j's S load.
-      auto load_k = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(&k_empty[st], ((j >> 1) & 1) ^ 1);
+      auto load_k = [&](int j, int tg) {
+        const int st = tg & 1;
+        mbar_wait(&k_empty[st], ((tg >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
         tma_load_2d(sK + st * TILE_BYTES, &tmap_qkv, &k_full[st], col_k, b * p.S + j * BKV);
       };
-      load_k(0);
-      for (int j = 0; j < nkv; ++j) {
-        if (j + 1 < nkv) load_k(j + 1);
-        mbar_wait(v_empty, (j & 1) ^ 1);
-        mbar_arrive_expect_tx(v_full, TILE_BYTES);
-        tma_load_2d(sV, &tmap_qkv, v_full, col_v, b * p.S + j * BKV);
+      for (int w = 0, t0 = 0; w < nitems; ++w) {
+        const int nkv = qb[w] + 1;               // causal: key tiles 0..qblk
+        mbar_wait(q_empty, (w & 1) ^ 1);
+        mbar_arrive_expect_tx(q_full, TILE_BYTES);
+        tma_load_2d(sQ, &tmap_qkv, q_full, col_q, b * p.S + qb[w] * BQ);
+        load_k(0, t0);
+        for (int j = 0; j < nkv; ++j) {
+          const int tg = t0 + j;
+          if (j + 1 < nkv) load_k(j + 1, tg + 1);
+          mbar_wait(v_empty, (tg & 1) ^ 1);
+          mbar_arrive_expect_tx(v_full, TILE_BYTES);
+          tma_load_2d(sV, &tmap_qkv, v_full, col_v, b * p.S + j * BKV);
+        }
+        t0 += nkv;
       }
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);   // S[128,128] = Q (K-major) x K^T (K-major)
     constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, D, 0, 1);     // O[128,64] = P (TMEM, K-major) x V (smem, MN-major)
-    mbar_wait(q_full, 0);
     const bool leader = elect_one();             // the same lane issues every MMA / commit of this CTA
     const uint64_t qd = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
     const uint64_t vd = make_smem_desc_sw128(smem_u32(sV), 16, 1024);
     const uint64_t kd0 = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
     const uint64_t kd1 = make_smem_desc_sw128(smem_u32(sK + TILE_BYTES), 16, 1024);
-    const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
-    // S_0 = Q K_0^T
-    mbar_wait(&k_full[0], 0);
-    tc_fence_after_sync();
-    if (leader) {
-      umma_ss(tS, qd, kd0, idesc_qk, 0u);
-      umma_ss(tS, qd + 2, kd0 + 2, idesc_qk, 1u);
-      umma_ss(tS, qd + 4, kd0 + 4, idesc_qk, 1u);
-      umma_ss(tS, qd + 6, kd0 + 6, idesc_qk, 1u);
-      umma_commit(s_full);
-      umma_commit(&k_empty[0]);
-    }
-    __syncwarp();
+    const bool dbg_cta = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+    auto issue_qk = [&](int tg, bool last) {
+      const int st = tg & 1;
+      mbar_wait(&k_full[st], (tg >> 1) & 1);
+      tc_fence_after_sync();
+      if (leader) {
+        const uint64_t kd = st ? kd1 : kd0;
+        umma_ss(tS, qd, kd, idesc_qk, 0u);
+        umma_ss(tS, qd + 2, kd + 2, idesc_qk, 1u);
+        umma_ss(tS, qd + 4, kd + 4, idesc_qk, 1u);
+        umma_ss(tS, qd + 6, kd + 6, idesc_qk, 1u);
+        umma_commit(s_full);
+        umma_commit(&k_empty[st]);               // K stage reusable once this QK retired
+        if (last) umma_commit(q_empty);          // ... and so is Q after the tile's last QK
+      }
+      __syncwarp();
+    };
+    for (int w = 0, t0 = 0; w < nitems; ++w) {
+    const int nkv = qb[w] + 1;
+    const bool dbg_on = dbg_cta && w == 0;
+    mbar_wait(q_full, w & 1);
+    if (w > 0) mbar_wait(s_free, (t0 - 1) & 1);  // the previous query tile's last S has been read
+    issue_qk(t0, nkv == 1);                      // S_0 = Q K_0^T
     for (int j = 0; j < nkv; ++j) {
+      const int tg = t0 + j;
       ATT_STAMP(8);
       // As soon as the softmax warps hold S_j in registers, the next QK^T goes into the same TMEM columns - it runs while
       // they compute the probabilities, so S_{j+1} is waiting for them when they come back.
       if (j + 1 < nkv) {
-        const int st = (j + 1) & 1;
-        mbar_wait(s_free, j & 1);
-        mbar_wait(&k_full[st], ((j + 1) >> 1) & 1);
-        tc_fence_after_sync();
-        if (leader) {
-          const uint64_t kd = st ? kd1 : kd0;
-          umma_ss(tS, qd, kd, idesc_qk, 0u);
-          umma_ss(tS, qd + 2, kd + 2, idesc_qk, 1u);
-          umma_ss(tS, qd + 4, kd + 4, idesc_qk, 1u);
-          umma_ss(tS, qd + 6, kd + 6, idesc_qk, 1u);
-          umma_commit(s_full);
-          umma_commit(&k_empty[st]);             // K stage reusable once this QK retired
-        }
-        __syncwarp();
+        mbar_wait(s_free, tg & 1);
+        issue_qk(tg + 1, j + 2 == nkv);
       }
       ATT_STAMP(9);
-      mbar_wait(p_full, j & 1);                  // P_j in tensor memory, O rescaled
+      mbar_wait(p_full, tg & 1);                 // P_j in tensor memory, O rescaled
       ATT_STAMP(10);
-      mbar_wait(v_full, j & 1);
+      mbar_wait(v_full, tg & 1);
       tc_fence_after_sync();
       if (leader) {
         // A operand straight from tensor memory: 16 keys of P = 8 columns per K step, no shared-memory read for A
@@ -240,18 +178,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       __syncwarp();
       ATT_STAMP(11);
     }
+    t0 += nkv;
+    }
   } else {
     // ------------------------------------------------------------------ softmax / correction / epilogue
     const int q = warp & 3;
     const int row = q * 32 + lane;               // query row inside the tile == TMEM lane
     const int half = (warp - 2) >> 2;            // 0: keys [0,64) of every tile and O columns [0,32) ; 1: the other halves
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    float m = -INFINITY, l = 0.f;                // l: this thread's half of the row sum
     const float c = p.scale_log2;
-    const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 64;
+    const bool dbg_cta = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 64;
+    for (int w = 0, t0 = 0; w < nitems; ++w) {
+    const int qblk = qb[w], nkv = qblk + 1;
+    const int row0 = b * p.S + qblk * BQ;        // first token row of this query tile
+    const bool dbg_on = dbg_cta && w == 0;
+    float m = -INFINITY, l = 0.f;                // l: this thread's half of the row sum
     for (int j = 0; j < nkv; ++j) {
+      const int tg = t0 + j;
       ATT_STAMP(0);
-      mbar_wait(s_full, j & 1);
+      mbar_wait(s_full, tg & 1);
       tc_fence_after_sync();
       ATT_STAMP(1);
       const bool diag = (j == qblk);
@@ -278,10 +223,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       }
       float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       // combine with the thread that owns the other 64 keys of this row
-      red[(j & 1) * 256 + half * 128 + row] = mx;
+      red[(tg & 1) * 256 + half * 128 + row] = mx;
       named_bar_sync(2, SOFTMAX_THREADS);
       ATT_STAMP(3);
-      mx = fmaxf(mx, red[(j & 1) * 256 + (half ^ 1) * 128 + row]);
+      mx = fmaxf(mx, red[(tg & 1) * 256 + (half ^ 1) * 128 + row]);
       // lazy rescaling: the reference point m only moves when the row maximum grew by more than 8 in the exp2 domain;
       // until then probabilities may exceed 1 (<= 2^8), which fp32 sums and bf16 P represent without trouble, and O / l
       // need no correction.  Both threads of a row see the same mx, so they take the same decision.
@@ -316,7 +261,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       m = mx;
       ATT_STAMP(4);
       if (j > 0) {
-        mbar_wait(o_done, (j - 1) & 1);          // PV_{j-1} retired: O is stable, P may be overwritten
+        mbar_wait(o_done, (tg - 1) & 1);         // PV_{j-1} retired: O is stable, P may be overwritten
         tc_fence_after_sync();
         // rescale this thread's 32 columns of the running output - skipped when no row of the warp moved its reference max
         if (!__all_sync(0xffffffffu, alpha == 1.f)) {
@@ -338,12 +283,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       if (lane == 0) mbar_arrive(p_full);
       ATT_STAMP(7);
     }
+    t0 += nkv;
     // ---- epilogue: total row sum = both halves
     named_bar_sync(2, SOFTMAX_THREADS);          // everyone is done reading the last tile's max exchange
     red[half * 128 + row] = l;
     named_bar_sync(2, SOFTMAX_THREADS);
     l += red[(half ^ 1) * 128 + row];
-    mbar_wait(o_done, (nkv - 1) & 1);
+    mbar_wait(o_done, (t0 - 1) & 1);
     tc_fence_after_sync();
     const float inv_l = 1.f / l;
     uint32_t r[32];
@@ -365,6 +311,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       tma_store_commit();
       tma_store_wait<0>();
     }
+    }  // query tiles of this CTA
   }
 
   tc_fence_before_sync();
@@ -395,7 +342,7 @@ ODB_EXPORT int odb_attn_fwd(const void* qkv, void* out, void* lse, int B, int S,
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  dim3 grid(S / BQ, Hq, B);
+  dim3 grid((S / BQ + 1) / 2, Hq, B);
   attn_fwd_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tq, to, p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
