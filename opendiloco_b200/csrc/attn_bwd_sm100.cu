@@ -5,18 +5,21 @@
 //   dS = P * (dP - D) * scale        D  = rowsum(dO * O)        (pre-pass kernel)
 //   dK = dS^T Q                      dQ = dS K                  (dQ: fp32 TMA reduce-add across key tiles, post-pass -> bf16)
 //
-// One CTA per (batch, kv-head, 128-key tile); it keeps K and V in shared memory and dK/dV accumulators in tensor memory
-// and walks over the query heads of its GQA group and the causal range of 128-query tiles.  Five GEMMs per tile pair, all
-// tcgen05.mma from shared-memory descriptors:
-//     S  = Q  K^T    A = Q  (K-major)   B = K  (K-major)    N = 128
-//     dP = dO V^T    A = dO (K-major)   B = V  (K-major)    N = 128
-//     dV += P^T  dO  A = P  (MN-major)  B = dO (MN-major)   N = 64      P, dS: bf16 tiles written by the softmax warps
-//     dK += dS^T Q   A = dS (MN-major)  B = Q  (MN-major)   N = 64
-//     dQ  = dS   K   A = dS (K-major)   B = K  (MN-major)   N = 64
+// One CTA per (batch, kv-head, PAIR of 128-key tiles {x, nq-1-x}) - every CTA runs the same number of iterations.  It
+// keeps K and V in shared memory and dK/dV accumulators in tensor memory and walks over the query heads of its GQA group
+// and the causal range of 128-query tiles.  The score tiles are computed TRANSPOSED (keys on the TMEM lanes) so that the
+// probabilities can feed the dV / dK GEMMs straight from tensor memory - shared-memory bandwidth (128 B/clk) is the
+// limiter of this kernel: an M128 N64 K16 MMA with both operands in smem needs 6 KB per 32 tensor cycles.
+//     S^T  = K  Q^T    A = K  (smem, K-major)   B = Q  (smem, K-major)   N = 128
+//     dP^T = V  dO^T   A = V  (smem, K-major)   B = dO (smem, K-major)   N = 128
+//     dV  += P^T  dO   A = P^T  (TMEM, bf16)    B = dO (smem, MN-major)  N = 64
+//     dK  += dS^T Q    A = dS^T (TMEM, bf16)    B = Q  (smem, MN-major)  N = 64
+//     dQ   = dS   K    A = dS^T tile in smem read MN-major               B = K (smem, MN-major)   N = 64
 // The same [128 x 64] swizzled tiles serve as K-major and as MN-major operands - only the descriptor changes.
-// TMEM: S [0,128) dP [128,256) dV [256,320) dK [320,384) dQ [384,448).   512 threads in four warpgroups with their own
-// register budgets (setmaxnreg): warp 0 TMA + warp 1 MMA (96 regs), warps 4-11 element-wise (two threads per query row,
-// 64 keys each; 160 regs) + dK/dV epilogue, warps 12-15 dQ drain (TMEM -> staging -> TMA reduce-add; 96 regs).
+// TMEM: S^T [0,128)  dP^T [128,256) - overwritten in place by P^T / dS^T (bf16, 2 queries per column) once read -
+// dV [256,320) dK [320,384) dQ [384,448).   512 threads in four warpgroups with their own register budgets (setmaxnreg):
+// warp 0 TMA + warp 1 MMA (96 regs), warps 4-11 element-wise (two threads per KEY row, 64 queries each; 160 regs) +
+// dK/dV epilogue, warps 12-15 dQ drain (TMEM -> staging -> TMA reduce-add; 96 regs).
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 #include "attn_math.cuh"
@@ -32,19 +35,29 @@ constexpr int TILE = 128 * 128;                  // bytes of a [128 x 64] bf16 t
 constexpr int THREADS = 512;                   // warp 0 TMA, 1 MMA, 2-3 idle | 4-11 element-wise | 12-15 dQ drain
 constexpr int EW_THREADS = 256, DRAIN_THREADS = 128;
 constexpr int EW_WARP0 = 4, DRAIN_WARP0 = 12;
-// K, V, 2 x (Q, dO), P (2 chunks), dS (2 chunks), dQ staging fp32 [128 x 64] = 2 chunks of 128 B rows
-constexpr int SMEM_BYTES = 2 * TILE + 4 * TILE + 2 * TILE + 2 * TILE + 2 * TILE + 1024 + 256;
+constexpr int QST = 3;                         // Q / dO / stats pipeline stages
+constexpr int STAT_BYTES = 2 * 128 * 4;        // per (b, h, query tile): -lse*log2(e) [128] then -D*scale [128]
+// K, V, QST x (Q, dO), dS^T (2 query chunks), dQ staging fp32 [128 x 64] = 2 chunks of 128 B rows, stats, barriers
+constexpr int SMEM_BYTES = 2 * TILE + 2 * QST * TILE + 2 * TILE + 2 * TILE + QST * STAT_BYTES + 1024 + 256;
 constexpr uint32_t TMEM_COLS = 512;
 
 struct Params {
   int B, S, Hq, Hkv;
   float scale, scale_log2;
-  const float* lse;      // [B, Hq, S] natural log (forward)
-  const float* dsum;     // [B, Hq, S] rowsum(dO * O)
+  const float* stats;    // [B, Hq, S/128, 2, 128] written by the pre-pass
   long long* dbg;        // optional timeline of CTA (0,0,0): [iteration][16] clock64 stamps (nullptr = off)
 };
 
 #define BWD_STAMP(slot) do { if (dbg_on) p.dbg[it * 16 + (slot)] = clock64(); } while (0)
+
+__device__ __forceinline__ void lds_2x64(uint32_t addr, uint64_t& a, uint64_t& b) {
+  asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+__device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
 
 template <int N>
 __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -59,19 +72,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
   uint8_t* sV = sK + TILE;
-  uint8_t* sQ = sV + TILE;                 // 2 stages
-  uint8_t* sdO = sQ + 2 * TILE;            // 2 stages
-  uint8_t* sP = sdO + 2 * TILE;            // [2 key-chunks][128 q rows][128 B]
-  uint8_t* sdS = sP + 2 * TILE;
+  uint8_t* sQ = sV + TILE;                 // QST stages
+  uint8_t* sdO = sQ + QST * TILE;          // QST stages
+  uint8_t* sdS = sdO + QST * TILE;         // dS^T: [2 query-chunks][128 key rows][128 B]  (also the dK/dV store staging)
   uint8_t* sdQ = sdS + 2 * TILE;           // fp32 staging: [2 column-chunks][128 rows][128 B]
-  uint64_t* kv_full = reinterpret_cast<uint64_t*>(sdQ + 2 * TILE);
+  float* sStat = reinterpret_cast<float*>(sdQ + 2 * TILE);   // QST x {-lse2[128], -dsum*scale[128]}
+  uint64_t* kv_full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStat) + QST * STAT_BYTES);
   uint64_t* kv_empty = kv_full + 1;        // the key tile's last MMAs retired: K / V may be replaced
-  uint64_t* q_full = kv_empty + 1;         // [2]
-  uint64_t* q_empty = q_full + 2;          // [2]
-  uint64_t* sdp_full = q_empty + 2;        // S and dP ready
-  uint64_t* sdp_free = sdp_full + 1;       // S and dP live in registers: the next S/dP MMAs may overwrite the columns (8 warps)
-  uint64_t* pds_full = sdp_free + 1;       // P and dS written to smem (8 warp arrivals)
-  uint64_t* mma_done = pds_full + 1;       // dV/dK/dQ MMAs of this iteration retired (P/dS buffers + dQ accumulator ready)
+  uint64_t* q_full = kv_empty + 1;         // [QST]
+  uint64_t* q_empty = q_full + QST;        // [QST]
+  uint64_t* s_full = q_empty + QST;        // S^T ready
+  uint64_t* dp_full = s_full + 1;          // dP^T ready (and every earlier MMA retired)
+  uint64_t* s_free = dp_full + 1;          // S^T lives in registers: the next S^T may overwrite the columns (8 warps)
+  uint64_t* pds_full = s_free + 1;         // P^T / dS^T in tensor memory, dS^T in shared memory (8 warp arrivals)
+  uint64_t* mma_done = pds_full + 1;       // dV/dK/dQ MMAs of this iteration retired (dQ accumulator ready)
   uint64_t* dq_empty = mma_done + 1;       // dQ accumulator drained (4 warp arrivals)
   uint64_t* dkv_empty = dq_empty + 1;      // dK/dV accumulators read by the epilogue (8 warp arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dkv_empty + 1);
@@ -79,7 +93,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nq = p.S / BQ;
   // Each CTA owns TWO key tiles of one (batch, kv head): tile x (nq-x query tiles to visit) and tile nq-1-x (x+1), so every
-  // CTA runs group*(nq+1) iterations - a balanced grid - and pays the fixed costs once.  `g` is the CTA-wide iteration
+  // CTA runs group*(nq+1) iterations - a balanced grid - and pays the fixed costs once.  `it` is the CTA-wide iteration
   // index all per-iteration barrier parities derive from.
   const int kb_first = (int)blockIdx.x, kb_second = nq - 1 - (int)blockIdx.x;
   const int nitems = kb_first != kb_second ? 2 : 1;
@@ -93,9 +107,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     tma_prefetch_desc(&tmap_do);
     mbar_init(kv_full, 1);
     mbar_init(kv_empty, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
-    mbar_init(sdp_full, 1);
-    mbar_init(sdp_free, 8);
+    for (int i = 0; i < QST; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(dp_full, 1);
+    mbar_init(s_free, 8);
     mbar_init(pds_full, 8);
     mbar_init(mma_done, 1);
     mbar_init(dq_empty, 4);
@@ -115,97 +130,110 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   if (warp < EW_WARP0) {
     reg_dealloc<96>();
     if (warp == 0 && lane == 0) {
-      {
-      for (int w = 0, g = 0; w < nitems; ++w) {
-        const int kb = w ? kb_second : kb_first;          // causal: query tiles kb..nq-1
+      int st = 0, ph = 0;                                // Q stage ring position / phase
+      for (int w = 0; w < nitems; ++w) {
+        const int kb = w ? kb_second : kb_first;         // causal: query tiles kb..nq-1
         mbar_wait(kv_empty, (w & 1) ^ 1);
         mbar_arrive_expect_tx(kv_full, 2 * TILE);
         tma_load_2d(sK, &tmap_qkv, kv_full, col_k, b * p.S + kb * BKV);
         tma_load_2d(sV, &tmap_qkv, kv_full, col_v, b * p.S + kb * BKV);
         for (int hh = 0; hh < group; ++hh) {
           const int h = hk * group + hh;
-          for (int qi = kb; qi < nq; ++qi, ++g) {
-            const int st = g & 1;
-            mbar_wait(&q_empty[st], ((g >> 1) & 1) ^ 1);
-            mbar_arrive_expect_tx(&q_full[st], 2 * TILE);
+          for (int qi = kb; qi < nq; ++qi) {
+            mbar_wait(&q_empty[st], ph ^ 1);
+            mbar_arrive_expect_tx(&q_full[st], 2 * TILE + STAT_BYTES);
             tma_load_2d(sQ + st * TILE, &tmap_qkv, &q_full[st], h * D, b * p.S + qi * BQ);
             tma_load_2d(sdO + st * TILE, &tmap_do, &q_full[st], h * D, b * p.S + qi * BQ);
+            bulk_load_1d(sStat + st * 256, p.stats + (((size_t)b * p.Hq + h) * nq + qi) * 256, STAT_BYTES, &q_full[st]);
+            if (++st == QST) { st = 0; ph ^= 1; }
           }
         }
       }
-    }
     } else if (warp == 1) {
-    constexpr uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);     // S, dP
-    constexpr uint32_t id_t = make_idesc_bf16(128, 64, 1, 1);      // dV, dK  (both operands MN-major)
-    constexpr uint32_t id_q = make_idesc_bf16(128, 64, 0, 1);      // dQ      (A K-major, B MN-major)
-    const bool leader = elect_one();
-    const uint64_t kd = make_smem_desc_sw128(smem_u32(sK), 16, 1024);        // K as K-major B (S) / MN-major B (dQ)
-    const uint64_t vd = make_smem_desc_sw128(smem_u32(sV), 16, 1024);
-    const uint64_t pd_mn = make_smem_desc_sw128(smem_u32(sP), TILE, 1024);   // P^T: 2 MN chunks (64 keys) TILE bytes apart
-    const uint64_t dsd_mn = make_smem_desc_sw128(smem_u32(sdS), TILE, 1024);
-    const uint64_t dsd_k0 = make_smem_desc_sw128(smem_u32(sdS), 16, 1024);   // dS as K-major A: key chunk 0 / 1
-    const uint64_t dsd_k1 = make_smem_desc_sw128(smem_u32(sdS + TILE), 16, 1024);
-    const bool dbg_on = dbg_cta && lane == 0;
-    // Software pipeline (the tensor pipe executes in issue order):
-    //   S/dP(g+1) is issued as soon as the element-wise warps hold S/dP(g) in registers, so it runs under their math;
-    //   dV/dK(g) follow once P/dS(g) are in shared memory, dQ(g) once the drain warps emptied the previous dQ tile.
-    auto issue_sdp = [&](int it) {
-      const int st = it & 1;
-      const uint64_t qd = make_smem_desc_sw128(smem_u32(sQ + st * TILE), 16, 1024);
-      const uint64_t dod = make_smem_desc_sw128(smem_u32(sdO + st * TILE), 16, 1024);
-      mbar_wait(&q_full[st], (it >> 1) & 1);
-      tc_fence_after_sync();
-      if (leader) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss(tS, qd + 2 * k, kd + 2 * k, id_s, k > 0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss(tdP, dod + 2 * k, vd + 2 * k, id_s, k > 0);
-        umma_commit(sdp_full);
-      }
-      __syncwarp();
-    };
-    for (int w = 0, g = 0; w < nitems; ++w) {
-      const int iters = group * (nq - (w ? kb_second : kb_first));
-      mbar_wait(kv_full, w & 1);
-      if (g > 0) mbar_wait(sdp_free, (g - 1) & 1);       // the previous key tile's last S/dP have been read
-      issue_sdp(g);
-      for (int i = 0; i < iters; ++i) {
-        const int it = g + i;
-        const int st = it & 1;
+      constexpr uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);     // S^T, dP^T
+      constexpr uint32_t id_ts = make_idesc_bf16(128, 64, 0, 1);     // dV, dK: A from tensor memory, B MN-major
+      constexpr uint32_t id_q = make_idesc_bf16(128, 64, 1, 1);      // dQ: both operands MN-major
+      const bool leader = elect_one();
+      const uint64_t kd = make_smem_desc_sw128(smem_u32(sK), 16, 1024);        // K as K-major A (S^T) / MN-major B (dQ)
+      const uint64_t vd = make_smem_desc_sw128(smem_u32(sV), 16, 1024);
+      const uint64_t dsd_mn = make_smem_desc_sw128(smem_u32(sdS), TILE, 1024);   // dS: 2 MN chunks (64 queries) TILE bytes apart
+      const bool dbg_on = dbg_cta && lane == 0;
+      int st = 0, ph = 0;                                // stage / phase of the NEXT S^T to issue
+      // Software pipeline (the tensor pipe executes in issue order):
+      //   S^T(it+1) is issued as soon as the element-wise warps hold S^T(it) in registers, so it runs under their math;
+      //   dV/dK(it) follow once P^T/dS^T(it) are in place, dQ(it) once the drain warps emptied the previous dQ tile, and
+      //   dP^T(it+1) goes last because it overwrites the columns P^T/dS^T(it) were read from.
+      auto issue_s = [&]() {
         const uint64_t qd = make_smem_desc_sw128(smem_u32(sQ + st * TILE), 16, 1024);
-        const uint64_t dod = make_smem_desc_sw128(smem_u32(sdO + st * TILE), 16, 1024);
-        BWD_STAMP(9);
-        if (i + 1 < iters) {
-          mbar_wait(sdp_free, it & 1);
-          issue_sdp(it + 1);
-        }
-        BWD_STAMP(10);
-        mbar_wait(pds_full, it & 1);                     // P, dS in shared memory
-        if (i == 0 && w > 0) mbar_wait(dkv_empty, (w - 1) & 1);   // the epilogue read the previous key tile's dK / dV
+        mbar_wait(&q_full[st], ph);
         tc_fence_after_sync();
-        BWD_STAMP(11);
-        const bool first = (i == 0);
         if (leader) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) umma_ss(tdV, pd_mn + 128 * k, dod + 128 * k, id_t, (first && k == 0) ? 0u : 1u);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) umma_ss(tdK, dsd_mn + 128 * k, qd + 128 * k, id_t, (first && k == 0) ? 0u : 1u);
+          for (int k = 0; k < 4; ++k) umma_ss(tS, kd + 2 * k, qd + 2 * k, id_s, k > 0);
+          umma_commit(s_full);
         }
         __syncwarp();
-        if (it > 0) mbar_wait(dq_empty, (it - 1) & 1);   // previous dQ tile drained
-        tc_fence_after_sync();
-        BWD_STAMP(12);
+      };
+      auto issue_dp = [&](int stg) {
+        const uint64_t dod = make_smem_desc_sw128(smem_u32(sdO + stg * TILE), 16, 1024);
         if (leader) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) umma_ss(tdQ, ((k >> 2) ? dsd_k1 : dsd_k0) + 2 * (k & 3), kd + 128 * k, id_q, k > 0);
-          umma_commit(&q_empty[st]);
-          umma_commit(mma_done);
-          if (i + 1 == iters) umma_commit(kv_empty);
+          for (int k = 0; k < 4; ++k) umma_ss(tdP, vd + 2 * k, dod + 2 * k, id_s, k > 0);
+          umma_commit(dp_full);
         }
         __syncwarp();
+      };
+      for (int w = 0, g = 0; w < nitems; ++w) {
+        const int iters = group * (nq - (w ? kb_second : kb_first));
+        mbar_wait(kv_full, w & 1);
+        if (g > 0) mbar_wait(s_free, (g - 1) & 1);       // the previous key tile's last S^T has been read
+        issue_s();
+        int cur = st;                                    // stage of iteration `it`
+        issue_dp(cur);
+        if (++st == QST) { st = 0; ph ^= 1; }
+        for (int i = 0; i < iters; ++i) {
+          const int it = g + i;
+          const uint64_t qd = make_smem_desc_sw128(smem_u32(sQ + cur * TILE), 16, 1024);
+          const uint64_t dod = make_smem_desc_sw128(smem_u32(sdO + cur * TILE), 16, 1024);
+          const int nxt = st;
+          BWD_STAMP(9);
+          if (i + 1 < iters) {
+            mbar_wait(s_free, it & 1);
+            issue_s();
+            if (++st == QST) { st = 0; ph ^= 1; }
+          }
+          BWD_STAMP(10);
+          mbar_wait(pds_full, it & 1);                   // P^T, dS^T in tensor memory; dS^T in shared memory
+          if (i == 0 && w > 0) mbar_wait(dkv_empty, (w - 1) & 1);   // the epilogue read the previous key tile's dK / dV
+          tc_fence_after_sync();
+          BWD_STAMP(11);
+          const bool first = (i == 0);
+          if (leader) {
+            // A straight from tensor memory: 16 queries = 8 columns per K step; the two query halves sit 64 columns apart
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              umma_ts(tdV, tdP + (k >> 2) * 64 + (k & 3) * 8, dod + 128 * k, id_ts, (first && k == 0) ? 0u : 1u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              umma_ts(tdK, tdP + 32 + (k >> 2) * 64 + (k & 3) * 8, qd + 128 * k, id_ts, (first && k == 0) ? 0u : 1u);
+          }
+          __syncwarp();
+          if (it > 0) mbar_wait(dq_empty, (it - 1) & 1); // previous dQ tile drained
+          tc_fence_after_sync();
+          BWD_STAMP(12);
+          if (leader) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) umma_ss(tdQ, dsd_mn + 128 * k, kd + 128 * k, id_q, k > 0);
+            umma_commit(&q_empty[cur]);
+            umma_commit(mma_done);
+            if (i + 1 == iters) umma_commit(kv_empty);
+          }
+          __syncwarp();
+          if (i + 1 < iters) issue_dp(nxt);
+          cur = nxt;
+        }
+        g += iters;
       }
-      g += iters;
-    }
     }
   } else if (warp >= DRAIN_WARP0) {
     reg_dealloc<96>();
@@ -257,87 +285,96 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     // ------------------------------------------------------------------ element-wise warps
     reg_alloc<160>();
     const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int half = (warp - EW_WARP0) >> 2;
+    const int row = q * 32 + lane;                       // KEY row inside the tile == TMEM lane
+    const int half = (warp - EW_WARP0) >> 2;             // queries [64*half, 64*half + 64) of the query tile
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const float c = p.scale_log2;
     const uint64_t c2 = pack2(c, c), sc2 = pack2(p.scale, p.scale);
     const bool elected = threadIdx.x == EW_WARP0 * 32;
     const bool dbg_on = dbg_cta && elected;
+    const uint32_t tPD = tdP + lane_off + half * 64;     // this thread's dP^T columns; P^T -> [0,32), dS^T -> [32,64) of them
+    int st = 0, ph = 0;
     for (int w = 0, it = 0; w < nitems; ++w) {
       const int kb = w ? kb_second : kb_first;
       for (int hh = 0; hh < group; ++hh) {
-        const int h = hk * group + hh;
         for (int qi = kb; qi < nq; ++qi, ++it) {
-          const size_t stat = ((size_t)b * p.Hq + h) * p.S + qi * BQ + row;
-          const float lse2 = p.lse[stat] * 1.4426950408889634f;
-          const float dsum = p.dsum[stat];
           const bool diag = (qi == kb);
+          const uint32_t stat = smem_u32(sStat + st * 256 + half * 64);
           BWD_STAMP(0);
-          mbar_wait(sdp_full, it & 1);
+          mbar_wait(&q_full[st], ph);                    // the statistics of this query tile are in shared memory
+          mbar_wait(s_full, it & 1);
           tc_fence_after_sync();
           BWD_STAMP(1);
-          uint32_t pp[32], ds[32];
+          uint32_t pp[32];
           {
-            uint32_t sr[64], dr[64];
+            uint32_t sr[64];
             tmem_ld_32x32b_x32(tS + lane_off + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
             tmem_ld_32x32b_x32(tS + lane_off + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
-            tmem_ld_32x32b_x32(tdP + lane_off + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&dr[0]));
-            tmem_ld_32x32b_x32(tdP + lane_off + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&dr[32]));
             tmem_ld_wait();
             tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(sdp_free);        // S/dP(it+1) may now be computed into the same columns
+            if (lane == 0) mbar_arrive(s_free);          // S^T(it+1) may now be computed into the same columns
             BWD_STAMP(2);
             if (diag) {
 #pragma unroll
               for (int i = 0; i < 64; ++i)
-                if (half * 64 + i > row) sr[i] = 0xff800000u;     // -inf -> P = 0
+                if (row > half * 64 + i) sr[i] = 0xff800000u;     // key after query: -inf -> P = 0
             }
-            // P = exp2(S*c - lse2), dS = P * (dP*scale - dsum*scale): packed fp32x2 math; of every four exponentials two
-            // go through the MUFU and two through the FMA-pipe polynomial (see attn_sm100.cu)
-            const uint64_t nl2 = pack2(-lse2, -lse2), nd2 = pack2(-dsum * p.scale, -dsum * p.scale);
+            // P = exp2(S*c - lse2[query]): packed fp32x2 math; of every four exponentials two go through the MUFU and two
+            // through the FMA-pipe polynomial (see attn_sm100.cu).  The per-query statistics are broadcast reads.
 #pragma unroll
             for (int i = 0; i < 64; i += 4) {
-              const uint64_t ya = ffma2(pack2u(sr[i], sr[i + 1]), c2, nl2);
-              const uint64_t yb = ffma2(pack2u(sr[i + 2], sr[i + 3]), c2, nl2);
+              uint64_t nla, nlb;
+              lds_2x64(stat + i * 4, nla, nlb);
+              const uint64_t ya = ffma2(pack2u(sr[i], sr[i + 1]), c2, nla);
+              const uint64_t yb = ffma2(pack2u(sr[i + 2], sr[i + 3]), c2, nlb);
               float a0, a1;
               unpack2(ya, a0, a1);
-              const uint64_t pa = pack2(fast_exp2(a0), fast_exp2(a1));
-              const uint64_t pb = poly_exp2x2(yb);
-              const uint64_t da = fmul2(pa, ffma2(pack2u(dr[i], dr[i + 1]), sc2, nd2));
-              const uint64_t db = fmul2(pb, ffma2(pack2u(dr[i + 2], dr[i + 3]), sc2, nd2));
-              pp[i / 2] = cvt_bf16x2(pa);
-              pp[i / 2 + 1] = cvt_bf16x2(pb);
-              ds[i / 2] = cvt_bf16x2(da);
-              ds[i / 2 + 1] = cvt_bf16x2(db);
+              pp[i / 2] = cvt_bf16x2(pack2(fast_exp2(a0), fast_exp2(a1)));
+              pp[i / 2 + 1] = cvt_bf16x2(poly_exp2x2(yb));
             }
           }
           BWD_STAMP(3);
-          if (it > 0) {
-            mbar_wait(mma_done, (it - 1) & 1);           // the previous tile's dV/dK/dQ MMAs no longer read P / dS
-            tc_fence_after_sync();
+          mbar_wait(dp_full, it & 1);                    // dP^T ready; every earlier MMA (dQ of the previous tile) retired
+          tc_fence_after_sync();
+          uint32_t ds[32];
+          {
+            uint32_t dr[64];
+            tmem_ld_32x32b_x32(tPD, *reinterpret_cast<uint32_t(*)[32]>(&dr[0]));
+            tmem_ld_32x32b_x32(tPD + 32, *reinterpret_cast<uint32_t(*)[32]>(&dr[32]));
+            tmem_ld_wait();
+            // dS = P * (dP*scale - D*scale): the bracket in packed fp32, the product in packed bf16 (the P the dV GEMM sees)
+#pragma unroll
+            for (int i = 0; i < 64; i += 4) {
+              uint64_t nda, ndb;
+              lds_2x64(stat + 512 + i * 4, nda, ndb);
+              ds[i / 2] = mul_bf16x2(pp[i / 2], cvt_bf16x2(ffma2(pack2u(dr[i], dr[i + 1]), sc2, nda)));
+              ds[i / 2 + 1] = mul_bf16x2(pp[i / 2 + 1], cvt_bf16x2(ffma2(pack2u(dr[i + 2], dr[i + 3]), sc2, ndb)));
+            }
           }
           if (w > 0 && hh == 0 && qi == kb) {
-            // P / dS doubled as the dK / dV store staging of the previous key tile: its TMA store must have read them
+            // the dS buffer doubled as the dK / dV store staging of the previous key tile: its TMA store must have read it
             if (elected) tma_store_wait_read<0>();
             named_bar_sync(1, EW_THREADS);
           }
           BWD_STAMP(4);
+          // P^T / dS^T -> tensor memory (A operands of dV / dK), dS^T -> shared memory (A operand of dQ, MN-major)
+          tmem_st_32x32b_x32(tPD, pp);
+          tmem_st_32x32b_x32(tPD + 32, ds);
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int off = half * TILE + row * 128 + ((u ^ (row & 7)) * 16);
-            *reinterpret_cast<uint4*>(sP + off) = make_uint4(pp[u * 4 + 0], pp[u * 4 + 1], pp[u * 4 + 2], pp[u * 4 + 3]);
-            *reinterpret_cast<uint4*>(sdS + off) = make_uint4(ds[u * 4 + 0], ds[u * 4 + 1], ds[u * 4 + 2], ds[u * 4 + 3]);
-          }
+          for (int u = 0; u < 8; ++u)
+            *reinterpret_cast<uint4*>(sdS + half * TILE + row * 128 + ((u ^ (row & 7)) * 16)) =
+                make_uint4(ds[u * 4 + 0], ds[u * 4 + 1], ds[u * 4 + 2], ds[u * 4 + 3]);
+          tmem_st_wait();
           fence_proxy_async_smem();
           tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(pds_full);
           BWD_STAMP(5);
+          if (++st == QST) { st = 0; ph ^= 1; }
         }
       }
-      // ---- dK / dV epilogue of this key tile: this thread's 32 columns -> bf16 -> staging (the P buffer) -> TMA store
+      // ---- dK / dV epilogue of this key tile: this thread's 32 columns -> bf16 -> staging (the dS buffer) -> TMA store
       mbar_wait(mma_done, (it - 1) & 1);
       tc_fence_after_sync();
       uint32_t r[32];
@@ -348,7 +385,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         float f[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[u * 8 + i]);
-        *reinterpret_cast<uint4*>(sP + row * 128 + (((half * 4 + u) ^ (row & 7)) * 16)) = pack8(f);
+        *reinterpret_cast<uint4*>(sdS + row * 128 + (((half * 4 + u) ^ (row & 7)) * 16)) = pack8(f);
       }
       tmem_ld_32x32b_x32(tdV + lane_off + half * 32, r);
       tmem_ld_wait();
@@ -360,13 +397,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         float f[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[u * 8 + i]);
-        *reinterpret_cast<uint4*>(sP + TILE + row * 128 + (((half * 4 + u) ^ (row & 7)) * 16)) = pack8(f);
+        *reinterpret_cast<uint4*>(sdS + TILE + row * 128 + (((half * 4 + u) ^ (row & 7)) * 16)) = pack8(f);
       }
       fence_proxy_async_smem();
       named_bar_sync(2, EW_THREADS);
       if (elected) {
-        tma_store_2d(&tmap_dk, sP, hk * D, b * p.S + kb * BKV);
-        tma_store_2d(&tmap_dv, sP + TILE, hk * D, b * p.S + kb * BKV);
+        tma_store_2d(&tmap_dk, sdS, hk * D, b * p.S + kb * BKV);
+        tma_store_2d(&tmap_dv, sdS + TILE, hk * D, b * p.S + kb * BKV);
         tma_store_commit();
       }
     }
@@ -378,20 +415,82 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   if (warp == 1) tmem_dealloc(tb, TMEM_COLS);
 }
 
-// D[b,h,s] = sum_d dO * O   (one warp per (token, head): 64 elements)
+// Pre-pass: per (token, head) D = sum_d dO * O, stored together with the forward's log-sum-exp in the layout the main
+// kernel bulk-copies per query tile: stats[b, h, s/128, 0, s%128] = -lse * log2(e), stats[..., 1, ...] = -D * scale.
+// Eight lanes per (token, head) (16 bytes of dO and O each); the same threads zero the fp32 dQ accumulator row.
 __global__ void __launch_bounds__(256) attn_dsum_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
-                                                        float* __restrict__ dsum, int B, int S, int Hq, long long ld) {
-  const int lane = threadIdx.x & 31;
-  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long total = (long long)B * S * Hq;
-  if (w >= total) return;
+                                                        const float* __restrict__ lse, float* __restrict__ stats,
+                                                        float* __restrict__ dq_acc, int B, int S, int Hq, long long ld, float scale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * S * Hq * 8;
+  if (i >= total) return;                                // total is a multiple of 8: whole lane groups leave together
+  const int sub = (int)(i & 7);
+  const long long w = i >> 3;
   const long long t = w / Hq;
   const int h = (int)(w % Hq);
-  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(dout + t * ld + h * 64 + lane * 2);
-  const __nv_bfloat162 o = *reinterpret_cast<const __nv_bfloat162*>(out + t * ld + h * 64 + lane * 2);
-  float s = __bfloat162float(a.x) * __bfloat162float(o.x) + __bfloat162float(a.y) * __bfloat162float(o.y);
-  s = warp_sum(s);
-  if (lane == 0) dsum[((t / S) * Hq + h) * S + (t % S)] = s;
+  float a[8], o[8];
+  unpack8(ld_v4(dout + t * ld + h * 64 + sub * 8), a);
+  unpack8(ld_v4(out + t * ld + h * 64 + sub * 8), o);
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s = fmaf(a[j], o[j], s);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  float4* z = reinterpret_cast<float4*>(dq_acc + (t * Hq + h) * 64 + sub * 8);
+  z[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+  z[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (sub == 0) {
+    const long long bb = t / S, ss = t % S;
+    float* dst = stats + (((bb * Hq + h) * (S / 128) + ss / 128) * 2) * 128 + (ss % 128);
+    dst[0] = -lse[(bb * Hq + h) * S + ss] * 1.4426950408889634f;
+    dst[128] = -s * scale;
+  }
+}
+
+// Post-pass: fp32 dQ accumulator -> bf16 into dq_out (row stride ld_out), and - when cos/sin tables are given - the
+// transpose RoPE rotation of dQ (on the way) and of dK (in place), so the packed dq|dk|dv buffer leaves ready for the
+// projection's dgrad / wgrad GEMMs.  One thread per 8 rotation pairs: x[j..j+8) and x[j+32..j+40) of one (token, head).
+__global__ void __launch_bounds__(256) attn_bwd_finish_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dq_out,
+                                                              __nv_bfloat16* __restrict__ dk, const float* __restrict__ cos_t,
+                                                              const float* __restrict__ sin_t, long long T, int S, int Hq, int Hkv,
+                                                              long long ld_out, long long ld_dk) {
+  const int H = Hq + (cos_t != nullptr ? Hkv : 0);
+  const long long total = T * H * 4;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int jv = (int)(i & 3);
+  const long long th = i >> 2;
+  const int head = (int)(th % H);
+  const long long t = th / H;
+  float a[8], b[8];
+  __nv_bfloat16* dst;
+  if (head < Hq) {
+    const float* src = dq_acc + (t * Hq + head) * 64 + jv * 8;
+    const float4 a0 = ld_f4(src), a1 = ld_f4(src + 4), b0 = ld_f4(src + 32), b1 = ld_f4(src + 36);
+    a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+    b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+    dst = dq_out + t * ld_out + head * 64 + jv * 8;
+  } else {
+    dst = dk + t * ld_dk + (head - Hq) * 64 + jv * 8;
+    unpack8(ld_v4(dst), a);
+    unpack8(ld_v4(dst + 32), b);
+  }
+  if (cos_t != nullptr) {
+    const int pos = (int)(t % S);
+    const float4 c0 = ld_f4(cos_t + (size_t)pos * 32 + jv * 8), c1 = ld_f4(cos_t + (size_t)pos * 32 + jv * 8 + 4);
+    const float4 s0 = ld_f4(sin_t + (size_t)pos * 32 + jv * 8), s1 = ld_f4(sin_t + (size_t)pos * 32 + jv * 8 + 4);
+    const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float x = a[j], y = b[j];
+      a[j] = x * cs[j] + y * sn[j];                      // rotation by -theta
+      b[j] = y * cs[j] - x * sn[j];
+    }
+  }
+  st_v4(dst, pack8(a));
+  st_v4(dst + 32, pack8(b));
 }
 
 }  // namespace attn_bwd
@@ -403,31 +502,35 @@ ODB_EXPORT int odb_attn_bwd_set_dbg(void* buf) {
   return 0;
 }
 
-// dq_acc: fp32 [T, Hq*64] ZERO-INITIALISED by the caller (accumulated with TMA reduce-add); dk, dv: bf16 [T, Hkv*64].
-ODB_EXPORT int odb_attn_bwd(const void* qkv, const void* out, const void* dout, const void* lse, void* dsum, void* dq_acc,
-                            void* dk, void* dv, int B, int S, int Hq, int Hkv, long long ld_qkv, long long ld_out,
-                            float softmax_scale, cudaStream_t st) {
+// stats: fp32 scratch of 2 * B * Hq * S elements (per-query statistics, written by the pre-pass);
+// dq_acc: fp32 [T, Hq*64] scratch (zeroed by the pre-pass, accumulated with TMA reduce-add);
+// dq, dk, dv: bf16 outputs with row strides ld_dq / ld_dkv elements - e.g. the three column blocks of one packed
+// [T, (Hq+2*Hkv)*64] buffer.  With cos/sin (fp32 [S, 32] tables) dq and dk leave with the RoPE rotation undone.
+ODB_EXPORT int odb_attn_bwd(const void* qkv, const void* out, const void* dout, const void* lse, void* stats, void* dq_acc,
+                            void* dq, void* dk, void* dv, const void* cos_t, const void* sin_t, int B, int S, int Hq, int Hkv,
+                            long long ld_qkv, long long ld_out, long long ld_dq, long long ld_dkv, float softmax_scale,
+                            cudaStream_t st) {
   using namespace attn_bwd;
-  if (S % BQ || Hq % Hkv || ld_qkv % 8 || ld_out % 8) return -1;
+  if (S % BQ || Hq % Hkv || ld_qkv % 8 || ld_out % 8 || ld_dq % 8 || ld_dkv % 8) return -1;
   const long long T = (long long)B * S;
   {
-    const long long warps = T * Hq;
-    attn_dsum_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)out, (float*)dsum,
-                                                                  B, S, Hq, ld_out);
+    const long long threads = T * Hq * 8;
+    attn_dsum_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)out,
+                                                                        (const float*)lse, (float*)stats, (float*)dq_acc, B, S, Hq,
+                                                                        ld_out, softmax_scale);
   }
   CUtensorMap tq, tdo, tdq, tdk, tdv;
   int rc;
   if ((rc = make_tmap_2d(&tq, qkv, T, (Hq + 2 * Hkv) * D, ld_qkv * 2, 128, 64, 2))) return rc;
   if ((rc = make_tmap_2d(&tdo, dout, T, Hq * D, ld_out * 2, 128, 64, 2))) return rc;
   if ((rc = make_tmap_2d(&tdq, dq_acc, T, Hq * D, (long long)Hq * D * 4, 128, 32, 4))) return rc;
-  if ((rc = make_tmap_2d(&tdk, dk, T, Hkv * D, (long long)Hkv * D * 2, 128, 64, 2))) return rc;
-  if ((rc = make_tmap_2d(&tdv, dv, T, Hkv * D, (long long)Hkv * D * 2, 128, 64, 2))) return rc;
+  if ((rc = make_tmap_2d(&tdk, dk, T, Hkv * D, ld_dkv * 2, 128, 64, 2))) return rc;
+  if ((rc = make_tmap_2d(&tdv, dv, T, Hkv * D, ld_dkv * 2, 128, 64, 2))) return rc;
   Params p{};
   p.B = B; p.S = S; p.Hq = Hq; p.Hkv = Hkv;
   p.scale = softmax_scale;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
-  p.lse = (const float*)lse;
-  p.dsum = (const float*)dsum;
+  p.stats = (const float*)stats;
   p.dbg = g_bwd_dbg;
   static bool attr_set = false;
   if (!attr_set) {
@@ -437,6 +540,12 @@ ODB_EXPORT int odb_attn_bwd(const void* qkv, const void* out, const void* dout, 
   }
   dim3 grid((S / BKV + 1) / 2, Hkv, B);
   attn_bwd_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tq, tdo, tdq, tdk, tdv, p);
+  {
+    const long long threads = T * (Hq + (cos_t ? Hkv : 0)) * 4;
+    attn_bwd_finish_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((const float*)dq_acc, (__nv_bfloat16*)dq,
+                                                                              (__nv_bfloat16*)dk, (const float*)cos_t,
+                                                                              (const float*)sin_t, T, S, Hq, Hkv, ld_dq, ld_dkv);
+  }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }

@@ -237,7 +237,8 @@ class LlamaEngine:
             wT_qkv = ar.wT(p + "self_attn.q_proj.weight", cfg.qkv_dim, h)
             parts_ok = attention_mask is None and wT_qkv is not None and cfg.q_dim % 64 == 0 and cfg.kv_dim % 64 == 0
             if attention_mask is None:
-                res = A.attention_bwd(ws.datt, ws.qkv[l], ws.att[l], ws.aux[l], ws.dqkv, B, S, Hq, Hkv, D, want_parts=parts_ok)
+                res = A.attention_bwd(ws.datt, ws.qkv[l], ws.att[l], ws.aux[l], ws.dqkv, B, S, Hq, Hkv, D, want_parts=parts_ok,
+                                      rope=(ws.cos, ws.sin))
             else:
                 _masked_attention_bwd(ws.datt, ws.aux[l], ws.dqkv, B, S, Hq, Hkv, D)
                 res = ws.dqkv
@@ -256,7 +257,8 @@ class LlamaEngine:
                     G.mm_tn_acc(dv, ws.xn1[l], gq[cfg.q_dim + cfg.kv_dim:])
                 TC.linear_a3(dq, dk, dv, wT_qkv, ws.dn)
             else:
-                K.rope_(ws.dqkv, ws.cos, ws.sin, S, Hq + Hkv, D, backward=True)
+                if attention_mask is not None or not A.bwd_applies_rope(ws.aux[l]):
+                    K.rope_(ws.dqkv, ws.cos, ws.sin, S, Hq + Hkv, D, backward=True)
                 G.mm_tn_acc(ws.dqkv, ws.xn1[l], ar.qkv_g(l))
                 G.mm_nn(ws.dqkv, ar.qkv_w(l), out=ws.dn, b_t=wT_qkv)
             K.rmsnorm_bwd(ws.dn, ws.xa[l], ar.w(p + "input_layernorm.weight"), ws.rstd1[l], ws.dx, ws.dx,

@@ -23,31 +23,63 @@ import ctypes
 from .. import _lib
 
 _FLASH = None
-_LIB = os.environ.get("ODB_ATTN_LIB", "cudnn")
-_TC_FWD = os.environ.get("ODB_TC_ATTN", "0") == "1"      # our tcgen05 forward kernel (csrc/attn_sm100.cu)
+# Back-end of the bf16 CUDA path: "tc" = our tcgen05 kernels (csrc/attn_sm100.cu, attn_bwd_sm100.cu; head_dim 64,
+# S % 128 == 0), "cudnn" / "flash" = the library kernels (kept as comparison baselines and for other head sizes).
+_LIB = os.environ.get("ODB_ATTN_LIB", "tc")
+
+
+def _tc_usable(qkv: torch.Tensor, S: int, Hq: int, Hkv: int, D: int) -> bool:
+    return (D == 64 and S % 128 == 0 and Hq % Hkv == 0 and qkv.dtype == torch.bfloat16 and qkv.stride(1) == 1
+            and qkv.stride(0) % 8 == 0 and _lib.has_symbol("odb_attn_fwd") and _lib.has_symbol("odb_attn_bwd"))
+
+
+def bwd_applies_rope(aux) -> bool:
+    """True when ``attention_bwd`` given ``rope=`` already undid the RoPE rotation of dq / dk (our kernels' post-pass)."""
+    return isinstance(aux[0], str) and aux[0] == "tc"
+
 _lib.register_optional("odb_attn_fwd", [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_int, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p])
 
 
-_lib.register_optional("odb_attn_bwd", [ctypes.c_void_p] * 8 + [ctypes.c_int] * 4 + [ctypes.c_longlong, ctypes.c_longlong, ctypes.c_float,
-                                                                                   ctypes.c_void_p])
+_lib.register_optional("odb_attn_bwd", [ctypes.c_void_p] * 11 + [ctypes.c_int] * 4 + [ctypes.c_longlong] * 4 + [ctypes.c_float, ctypes.c_void_p])
+_SCRATCH: dict = {}
+
+
+def _bwd_scratch(dev, T: int, Hq: int, D: int):
+    """fp32 dQ accumulator + per-query statistics of the backward kernel (reused across layers / steps: every call
+    rewrites them completely before reading)."""
+    key = (dev, T, Hq, D)
+    sc = _SCRATCH.get(key)
+    if sc is None:
+        sc = (torch.empty(T, Hq * D, dtype=torch.float32, device=dev), torch.empty(2 * T * Hq, dtype=torch.float32, device=dev))
+        _SCRATCH[key] = sc
+    return sc
 
 
 def tc_attention_bwd(dout: torch.Tensor, qkv: torch.Tensor, out: torch.Tensor, lse: torch.Tensor, B: int, S: int, Hq: int, Hkv: int,
-                     D: int = 64):
-    """Our tcgen05 attention backward.  Returns (dq [T,Hq*D] bf16, dk [T,Hkv*D] bf16, dv [T,Hkv*D] bf16)."""
+                     D: int = 64, dqkv: torch.Tensor | None = None, cos: torch.Tensor | None = None, sin: torch.Tensor | None = None):
+    """Our tcgen05 attention backward (csrc/attn_bwd_sm100.cu): pre-pass (row statistics, zero dQ accumulator), main
+    kernel, post-pass (dQ fp32 -> bf16).  With ``dqkv`` the three gradients land in the column blocks of that packed
+    [T, (Hq+2*Hkv)*D] buffer (returned); otherwise returns dense (dq, dk, dv).  With ``cos``/``sin`` the post-pass also
+    undoes the RoPE rotation of dq and dk (the backward of the fused QKV+RoPE projection epilogue)."""
     assert D == 64 and S % 128 == 0 and dout.is_contiguous() and out.is_contiguous()
     T = B * S
     dev = qkv.device
-    dq_acc = torch.zeros(T, Hq * D, dtype=torch.float32, device=dev)       # accumulated across key tiles by TMA reduce-add
-    dk = torch.empty(T, Hkv * D, dtype=qkv.dtype, device=dev)
-    dv = torch.empty(T, Hkv * D, dtype=qkv.dtype, device=dev)
-    dsum = torch.empty(B, Hq, S, dtype=torch.float32, device=dev)
-    _lib.check(_lib.cuda_lib().odb_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dsum.data_ptr(),
-                                            dq_acc.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, S, Hq, Hkv, qkv.stride(0),
-                                            out.stride(0), 1.0 / math.sqrt(D), _lib.stream_ptr(qkv)), "attn_bwd")
-    _lib.count_launch(2)
-    return dq_acc.to(qkv.dtype), dk, dv
+    dq_acc, stats = _bwd_scratch(dev, T, Hq, D)
+    if dqkv is not None:
+        dq, dk, dv = dqkv[:, : Hq * D], dqkv[:, Hq * D:(Hq + Hkv) * D], dqkv[:, (Hq + Hkv) * D:]
+    else:
+        dq = torch.empty(T, Hq * D, dtype=qkv.dtype, device=dev)
+        dk = torch.empty(T, Hkv * D, dtype=qkv.dtype, device=dev)
+        dv = torch.empty(T, Hkv * D, dtype=qkv.dtype, device=dev)
+    assert dk.stride(0) == dv.stride(0)
+    _lib.check(_lib.cuda_lib().odb_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), stats.data_ptr(),
+                                            dq_acc.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                                            cos.data_ptr() if cos is not None else None, sin.data_ptr() if sin is not None else None,
+                                            B, S, Hq, Hkv, qkv.stride(0), out.stride(0), dq.stride(0), dk.stride(0),
+                                            1.0 / math.sqrt(D), _lib.stream_ptr(qkv)), "attn_bwd")
+    _lib.count_launch(3)
+    return dqkv if dqkv is not None else (dq, dk, dv)
 
 
 def tc_attention_fwd(qkv: torch.Tensor, B: int, S: int, Hq: int, Hkv: int, D: int = 64, dbg: torch.Tensor | None = None):
@@ -86,7 +118,10 @@ def attention_fwd(qkv: torch.Tensor, B: int, S: int, Hq: int, Hkv: int, D: int):
     q, k, v = split_qkv(qkv, B, S, Hq, Hkv, D)
     scale = 1.0 / math.sqrt(D)
     if qkv.is_cuda and qkv.dtype in (torch.bfloat16, torch.float16):
-        if _LIB == "cudnn":
+        if _LIB == "tc" and _tc_usable(qkv, S, Hq, Hkv, D):
+            out, lse = tc_attention_fwd(qkv, B, S, Hq, Hkv, D)
+            return out, ("tc", lse)
+        if _LIB != "flash":
             r = torch.ops.aten._scaled_dot_product_cudnn_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), None,
                                                                    True, 0.0, True, False, scale=scale)
             out = r[0].transpose(1, 2)          # cuDNN keeps the [B,S,H,D] memory layout of q
@@ -110,9 +145,13 @@ def attention_fwd(qkv: torch.Tensor, B: int, S: int, Hq: int, Hkv: int, D: int):
 
 
 def attention_bwd(dout: torch.Tensor, qkv: torch.Tensor, out: torch.Tensor, aux, dqkv: torch.Tensor, B: int, S: int,
-                  Hq: int, Hkv: int, D: int, want_parts: bool = False):
+                  Hq: int, Hkv: int, D: int, want_parts: bool = False, rope=None):
     """Writes dq|dk|dv into the packed ``dqkv`` buffer (same layout as qkv) and returns it - or, with ``want_parts`` and a
-    back-end that produces separate dense gradients, returns the tuple (dq [T,Hq*D], dk [T,Hkv*D], dv [T,Hkv*D])."""
+    back-end that produces separate dense gradients, returns the tuple (dq [T,Hq*D], dk [T,Hkv*D], dv [T,Hkv*D]).
+    ``rope=(cos, sin)``: a back-end for which ``bwd_applies_rope(aux)`` holds also undoes the rotation of dq / dk."""
+    if isinstance(aux[0], str) and aux[0] == "tc":
+        cos, sin = rope if rope is not None else (None, None)
+        return tc_attention_bwd(dout, qkv, out, aux[1], B, S, Hq, Hkv, D, dqkv=dqkv, cos=cos, sin=sin)
     q, k, v = split_qkv(qkv, B, S, Hq, Hkv, D)
     dq, dk, dv = split_qkv(dqkv, B, S, Hq, Hkv, D)
     scale = 1.0 / math.sqrt(D)

@@ -2,6 +2,7 @@
 import math, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from opendiloco_b200.ops import attention as A
+A._LIB = "cudnn"      # attention_fwd / attention_bwd below = the cuDNN baseline; the tc_* entry points are ours
 dev = "cuda"
 def timeit(fn, n=10):
     for _ in range(2): fn()
@@ -32,7 +33,8 @@ for (B, S, Hq, Hkv) in [(1, 128, 1, 1), (1, 256, 1, 1), (2, 256, 4, 2), (2, 1024
         res = A.attention_bwd(dout, qkv, o2, aux, torch.empty_like(qkv), B, S, Hq, Hkv, 64, want_parts=True)
         msg += f" vs cudnn: dq {rel(dq, res[0]):.2e} dk {rel(dk, res[1]):.2e} dv {rel(dv, res[2]):.2e}"
         fl = 2.5 * 4 * S * S * Hq * 64 * B / 2
-        t1 = timeit(lambda: A.tc_attention_bwd(dout, qkv, out, lse, B, S, Hq, Hkv))
+        packed = torch.empty_like(qkv)
+        t1 = timeit(lambda: A.tc_attention_bwd(dout, qkv, out, lse, B, S, Hq, Hkv, dqkv=packed))   # pre-pass + main + post-pass
         t0 = timeit(lambda: A.attention_bwd(dout, qkv, o2, aux, torch.empty_like(qkv), B, S, Hq, Hkv, 64, want_parts=True))
         msg += f" | ours {t1*1e3:.0f}us {fl/t1/1e9:.0f} TF/s | cudnn {t0*1e3:.0f}us {fl/t0/1e9:.0f} TF/s"
     print(msg, flush=True)

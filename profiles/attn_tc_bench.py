@@ -2,6 +2,7 @@
 import math, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from opendiloco_b200.ops import attention as A
+A._LIB = "cudnn"      # attention_fwd / attention_bwd below = the cuDNN baseline; the tc_* entry points are ours
 dev = "cuda"
 def timeit(fn, n=10):
     for _ in range(3): fn()
