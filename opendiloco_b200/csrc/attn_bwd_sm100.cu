@@ -22,11 +22,11 @@
 // dK/dV epilogue, warps 12-15 dQ drain (TMEM -> staging -> TMA reduce-add; 96 regs).
 #include "common.cuh"
 #include "sm100_ptx.cuh"
-#include "attn_math.cuh"
+#include "packed_math.cuh"
 
 using namespace odb;
 using namespace sm100;
-using namespace attn_math;
+using namespace packed_math;
 
 namespace attn_bwd {
 

@@ -14,11 +14,11 @@
 //              epilogue: O / l -> bf16 -> swizzled staging tile -> TMA store
 #include "common.cuh"
 #include "sm100_ptx.cuh"
-#include "attn_math.cuh"
+#include "packed_math.cuh"
 
 using namespace odb;
 using namespace sm100;
-using namespace attn_math;
+using namespace packed_math;
 
 namespace attn {
 

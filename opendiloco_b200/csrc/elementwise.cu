@@ -54,20 +54,40 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const __nv_bfloat16* x
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int nvec = h / 8;
-  for (int t = blockIdx.x * warps_per_block + (threadIdx.x >> 5); t < T; t += gridDim.x * warps_per_block) {
-    const uint4* xr = reinterpret_cast<const uint4*>(x_in + (size_t)t * h);
+  // rows are software-pipelined: the next token's x / delta rows are requested before the current one is reduced
+  const int stride = gridDim.x * warps_per_block;
+  int t = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  constexpr bool kPipe = NCH <= 4;
+  uint4 nxv[NCH], ndv[NCH];
+  auto fetch = [&](int tt) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x_in + (size_t)tt * h);
+    const uint4* dr = delta ? reinterpret_cast<const uint4*>(delta + (size_t)tt * h) : nullptr;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c = lane + k * 32;
+      if (c < nvec) {
+        nxv[k] = ld_v4(xr + c);
+        if (dr) ndv[k] = ld_nc_v4(dr + c);
+      }
+    }
+  };
+  if (kPipe && t < T) fetch(t);
+  for (; t < T; t += stride) {
+    if constexpr (!kPipe) fetch(t);
     uint4* xo = reinterpret_cast<uint4*>(x_out + (size_t)t * h);
-    const uint4* dr = delta ? reinterpret_cast<const uint4*>(delta + (size_t)t * h) : nullptr;
     float v[NCH][8];
+    uint4 cdv[NCH];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) { unpack8(nxv[k], v[k]); cdv[k] = ndv[k]; }
+    if (kPipe && t + stride < T) fetch(t + stride);      // (x_out may alias x_in: rows of different tokens never overlap)
     float ss = 0.f;
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
       const int c = lane + k * 32;
       if (c < nvec) {
-        unpack8(ld_v4(xr + c), v[k]);
-        if (dr) {
+        if (delta) {
           float d[8];
-          unpack8(ld_nc_v4(dr + c), d);
+          unpack8(cdv[k], d);
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[k][j] = bf16_round(v[k][j] + d[j]);
           st_v4(xo + c, pack8(v[k]));
@@ -123,18 +143,42 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const __nv_bfloat16* _
     for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
   const uint4* wr = reinterpret_cast<const uint4*>(w);
 
-  for (int t = blockIdx.x * warps_per_block + (threadIdx.x >> 5); t < T; t += gridDim.x * warps_per_block) {
-    const uint4* dyr = reinterpret_cast<const uint4*>(dy + (size_t)t * h);
-    const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)t * h);
-    const float r = rstd[t];
-    uint4 rdy[NCH], rx[NCH];  // rows stay packed (bf16) in registers between the two passes
+  // The rows of a warp are software-pipelined: the three input rows of the NEXT token are requested before the current
+  // one is processed, so loads stay in flight during the arithmetic (a warp owns ~14 rows; without this every row pays
+  // a full memory latency).  Rows stay packed (bf16) in registers between the two passes.
+  const int stride = gridDim.x * warps_per_block;
+  int t = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  uint4 ndy[NCH], nx[NCH], nres[NCH];
+  float nr = 0.f;
+  auto fetch = [&](int tt) {
+    const uint4* dyr = reinterpret_cast<const uint4*>(dy + (size_t)tt * h);
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)tt * h);
+    const uint4* dir = dres_in ? reinterpret_cast<const uint4*>(dres_in + (size_t)tt * h) : nullptr;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c = lane + k * 32;
+      if (c < nvec) {
+        ndy[k] = ld_nc_v4(dyr + c);
+        nx[k] = ld_nc_v4(xr + c);
+        if (dir) nres[k] = ld_v4(dir + c);
+      }
+    }
+    nr = rstd[tt];
+  };
+  constexpr bool kPipe = NCH <= 4;            // wider rows do not have the registers for a second row in flight
+  if (kPipe && t < T) fetch(t);
+  for (; t < T; t += stride) {
+    if constexpr (!kPipe) fetch(t);
+    uint4 rdy[NCH], rx[NCH], rres[NCH];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) { rdy[k] = ndy[k]; rx[k] = nx[k]; rres[k] = nres[k]; }
+    const float r = nr;
+    if (kPipe && t + stride < T) fetch(t + stride);
     float dot = 0.f;
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
       const int c = lane + k * 32;
       if (c < nvec) {
-        rdy[k] = ld_nc_v4(dyr + c);
-        rx[k] = ld_nc_v4(xr + c);
         float d[8], xv[8], wv[8];
         unpack8(rdy[k], d);
         unpack8(rx[k], xv);
@@ -150,7 +194,6 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const __nv_bfloat16* _
       }
     }
     dot = warp_sum(dot) / (float)h;
-    const uint4* dir = dres_in ? reinterpret_cast<const uint4*>(dres_in + (size_t)t * h) : nullptr;
     uint4* dor = reinterpret_cast<uint4*>(dres_out + (size_t)t * h);
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
@@ -162,9 +205,9 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const __nv_bfloat16* _
         unpack8(ld_v4(wr + c), wv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = r * (d[j] * wv[j] - xv[j] * r * dot);
-        if (dir) {
+        if (dres_in) {
           float p[8];
-          unpack8(ld_v4(dir + c), p);
+          unpack8(rres[k], p);
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] += p[j];
         }
@@ -326,6 +369,7 @@ ODB_EXPORT int odb_embedding_bwd(const void* ids, const void* dout, void* dW, in
     const int _n = ceil_div((h), 256);                             \
     if (_n <= 1) { constexpr int NCH = 1; __VA_ARGS__; }           \
     else if (_n <= 2) { constexpr int NCH = 2; __VA_ARGS__; }      \
+    else if (_n <= 3) { constexpr int NCH = 3; __VA_ARGS__; }      \
     else if (_n <= 4) { constexpr int NCH = 4; __VA_ARGS__; }      \
     else if (_n <= 8) { constexpr int NCH = 8; __VA_ARGS__; }      \
     else if (_n <= 16) { constexpr int NCH = 16; __VA_ARGS__; }    \

@@ -19,6 +19,8 @@
 //   kStore   : plain bf16 store
 //   kSwiGLU  : B rows are [gate rows n0..n0+127 | up rows I+n0..I+n0+127]; writes gate|up (needed by backward) AND
 //              act = silu(gate) * up, so the SwiGLU kernel and its re-read of the 2I-wide tensor disappear
+//   kSwiGLUBwd: the GEMM result is d(act) of the down projection; the epilogue TMA-loads the matching gate / up tiles of
+//              C = gu [M, 2I], turns them IN PLACE into d(gate) / d(up) and stores them back - d(act) never reaches memory
 //   kRoPE    : C is the packed qkv buffer; 64-column chunks are heads; chunks below `rope_cols` are rotated with the
 //              HF rotate-half convention using fp32 cos/sin tables (position = row % S)
 #include "common.cuh"
@@ -40,10 +42,11 @@ constexpr int EPI_GROUPS = 2;
 constexpr int GROUP_M = 16;           // rasterisation: 16 m-blocks x all n-blocks per super-block (L2 reuse of A and B)
 constexpr uint32_t TMEM_COLS = 512;
 
-enum Epi { kStore = 0, kSwiGLU = 1, kRoPE = 2 };
+enum Epi { kStore = 0, kSwiGLU = 1, kRoPE = 2, kSwiGLUBwd = 3 };
 
 template <int EPI> struct Cfg { static constexpr int STAGES = 5, NBUF = 4; };     // NBUF: staging tiles (2 per epilogue group)
 template <> struct Cfg<kSwiGLU> { static constexpr int STAGES = 4, NBUF = 6; };   // 3 per epilogue group
+template <> struct Cfg<kSwiGLUBwd> { static constexpr int STAGES = 3, NBUF = 8; };   // per group: 2 chunks x (gate, up) in/out tiles
 
 template <int EPI>
 constexpr int smem_bytes() { return Cfg<EPI>::STAGES * (A_BYTES + B_BYTES) + Cfg<EPI>::NBUF * EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/; }
@@ -97,7 +100,8 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* gu_full = tmem_empty + 2;                    // kSwiGLUBwd: [group][chunk] gate/up tiles landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gu_full + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();          // 0 = leader of the pair
@@ -111,6 +115,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     tma_prefetch_desc(&tmap_c);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 16); }   // 8 epilogue warps x 2 CTAs
+    for (int i = 0; i < 4; ++i) mbar_init(&gu_full[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_2cta(tmem_slot, TMEM_COLS);
@@ -184,6 +189,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     uint8_t* my_epi = smem_epi + eg * (NBUF / EPI_GROUPS) * EPI_BYTES;
     int it = 0;
     int buf_i = 0;
+    uint32_t gu_phase = 0;                        // kSwiGLUBwd: phase bit per chunk slot (a ragged tile skips a slot)
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -191,6 +197,22 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       tile_coords(tile, p.num_m, p.num_n, m_blk, n_blk);
       const int m_idx = m_blk * (2 * BM) + (int)cta_rank * BM;
       const uint32_t leader_tmem_empty = mapa_shared(smem_u32(&tmem_empty[acc]), 0);
+      if constexpr (EPI == kSwiGLUBwd) {
+        // fetch this group's gate / up tiles while the accumulator is still being computed.  The staging tiles are the
+        // ones the previous tile's stores read from, so those must have drained first.
+        if (store_thread) {
+          tma_store_wait_read<0>();
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int col = n_blk * BN + (eg + 2 * k) * 64;
+            if (col >= p.I) continue;                    // ragged last tile (I % 256 != 0): chunk lies beyond the gate block
+            uint64_t* bar = &gu_full[eg * 2 + k];
+            mbar_arrive_expect_tx(bar, 2 * EPI_BYTES);
+            tma_load_2d(my_epi + (2 * k) * EPI_BYTES, &tmap_c, bar, col, m_idx);
+            tma_load_2d(my_epi + (2 * k + 1) * EPI_BYTES, &tmap_c, bar, p.I + col, m_idx);
+          }
+        }
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
@@ -238,6 +260,54 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             tma_store_2d(&tmap_c, bg, n0 + c * 64, m_idx);
             tma_store_2d(&tmap_c, bu, p.I + n0 + c * 64, m_idx);
             tma_store_2d(&tmap_aux, ba, n0 + c * 64, m_idx);
+            tma_store_commit();
+          }
+        }
+      } else if constexpr (EPI == kSwiGLUBwd) {
+#pragma unroll 1
+        for (int k = 0; k < 2; ++k) {
+          const int c = eg + 2 * k;
+          float d[64];
+          {
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32b_x32(t_row + c * 64, r0);
+            tmem_ld_32x32b_x32(t_row + c * 64 + 32, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { d[j] = __uint_as_float(r0[j]); d[32 + j] = __uint_as_float(r1[j]); }
+          }
+          if (k == 1) {                                  // this warp's last chunk of the tile
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(leader_tmem_empty);
+          }
+          if (n_blk * BN + c * 64 >= p.I) continue;      // nothing was loaded for this chunk, nothing to store
+          mbar_wait(&gu_full[eg * 2 + k], (gu_phase >> k) & 1);
+          gu_phase ^= 1u << k;
+          uint8_t* bg = my_epi + (2 * k) * EPI_BYTES + row * 128;
+          uint8_t* bu = my_epi + (2 * k + 1) * EPI_BYTES + row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int phys = (j ^ (row & 7)) * 16;
+            float g[8], u[8], og[8], ou[8];
+            unpack8(*reinterpret_cast<const uint4*>(bg + phys), g);
+            unpack8(*reinterpret_cast<const uint4*>(bu + phys), u);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float dj = bf16_round(d[j * 8 + e]);           // the un-fused path rounds d(act) to bf16 first
+              const float sg = __fdividef(1.f, 1.f + __expf(-g[e]));
+              og[e] = dj * u[e] * sg * (1.f + g[e] * (1.f - sg));
+              ou[e] = dj * g[e] * sg;
+            }
+            *reinterpret_cast<uint4*>(bg + phys) = pack8(og);
+            *reinterpret_cast<uint4*>(bu + phys) = pack8(ou);
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(bar_b, EPI_THREADS);
+          if (store_thread) {
+            const int col = n_blk * BN + c * 64;
+            tma_store_2d(&tmap_c, my_epi + (2 * k) * EPI_BYTES, col, m_idx);
+            tma_store_2d(&tmap_c, my_epi + (2 * k + 1) * EPI_BYTES, p.I + col, m_idx);
             tma_store_commit();
           }
         }
@@ -318,7 +388,7 @@ static int launch(const void* A, const void* B, void* C, void* aux, int M, int N
                   cudaStream_t st, const ASplit& sp = ASplit()) {
   CUtensorMap ta, tb, tc, tx, ta1, ta2;
   int rc;
-  const int n_out = (EPI == kSwiGLU) ? 2 * I : N;
+  const int n_out = (EPI == kSwiGLU || EPI == kSwiGLUBwd) ? 2 * I : N;
   if ((rc = make_tmap_2d(&ta, A, M, sp.K0 ? sp.K0 : K, lda * 2, BM, BK, 2))) return rc;
   ta1 = ta; ta2 = ta;
   if (sp.K0) {
@@ -367,6 +437,14 @@ ODB_EXPORT int odb_gemm2_bf16_tn(const void* A, const void* B, void* C, int M, i
 ODB_EXPORT int odb_gemm2_swiglu(const void* X, const void* Wgu, void* gu, void* act, int M, int I, int K, cudaStream_t st) {
   if (K % 8 || I % 64) return -1;
   return gemm2::launch<gemm2::kSwiGLU>(X, Wgu, gu, act, M, 2 * I, K, K, K, 2 * I, I, I, 0, 0, nullptr, nullptr, st);
+}
+
+// Backward of the SwiGLU MLP's middle: gu[M,2I] (gate|up, bf16) is replaced IN PLACE by d(gate)|d(up), where
+// d(act)[M,I] = dY[M,K] * WdT[I,K]^T is formed in tensor memory only (I % 64 == 0).
+ODB_EXPORT int odb_gemm2_swiglu_bwd(const void* dY, const void* WdT, void* gu, int M, int I, int K, long long lda, long long ldb,
+                                    cudaStream_t st) {
+  if (K % 8 || I % 64 || lda % 8 || ldb % 8) return -1;
+  return gemm2::launch<gemm2::kSwiGLUBwd>(dY, WdT, gu, nullptr, M, I, K, lda, ldb, 2 * I, 0, I, 0, 0, nullptr, nullptr, st);
 }
 
 // qkv[M,N] = x[M,K] * Wqkv[N,K]^T with RoPE applied to the first rope_cols columns (head_dim 64, position = row % S)

@@ -1,8 +1,8 @@
-// Packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2 / FMUL2) and exp2 helpers shared by the attention kernels.
+// Packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2 / FMUL2) and exp2 helpers shared by the attention and cross-entropy kernels.
 #pragma once
 #include "common.cuh"
 
-namespace attn_math {
+namespace packed_math {
 using namespace odb;
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -84,4 +84,4 @@ __device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
   return d;
 }
 
-}  // namespace attn_math
+}  // namespace packed_math

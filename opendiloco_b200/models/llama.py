@@ -225,8 +225,12 @@ class LlamaEngine:
             p = f"model.layers.{l}."
             # ---- MLP block (ws.dx is the gradient of x_out = xm + down(act))
             G.mm_tn_acc(ws.dx, ws.act[l], ar.g(p + "mlp.down_proj.weight"))
-            G.mm_nn(ws.dx, ar.w(p + "mlp.down_proj.weight"), out=ws.dact, b_t=ar.wT(p + "mlp.down_proj.weight", h, i))
-            K.swiglu_bwd(ws.dact, ws.gu[l], ws.gu[l])                      # in place: gu <- d(gu)
+            wT_down = ar.wT(p + "mlp.down_proj.weight", h, i)
+            if TC.swiglu_bwd_usable(ws.dx, wT_down, ws.gu[l]):
+                TC.linear_swiglu_bwd(ws.dx, wT_down, ws.gu[l])             # dgrad GEMM with the SwiGLU backward as epilogue
+            else:
+                G.mm_nn(ws.dx, ar.w(p + "mlp.down_proj.weight"), out=ws.dact, b_t=wT_down)
+                K.swiglu_bwd(ws.dact, ws.gu[l], ws.gu[l])                  # in place: gu <- d(gu)
             G.mm_tn_acc(ws.gu[l], ws.xn2[l], ar.gu_g(l))
             G.mm_nn(ws.gu[l], ar.gu_w(l), out=ws.dn, b_t=ar.wT(p + "mlp.gate_proj.weight", 2 * i, h))
             K.rmsnorm_bwd(ws.dn, ws.xm[l], ar.w(p + "post_attention_layernorm.weight"), ws.rstd2[l], ws.dx, ws.dx,

@@ -29,7 +29,10 @@ _lib.register_optional("odb_gemm2_bf16_tn_a3", [c_void_p, c_void_p, c_void_p, c_
 _lib.register_optional("odb_wgrad_bf16", [c_void_p, c_void_p, c_void_p, c_ll, c_ll, c_ll, c_int, c_int, c_int, c_void_p, c_ll, c_void_p,
                                          c_ll, c_int, c_int, c_void_p])
 
+_lib.register_optional("odb_gemm2_swiglu_bwd", [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_ll, c_ll, c_void_p])
+
 ENABLED = os.environ.get("ODB_TC_GEMM", "1") != "0"
+FUSE_SWIGLU_BWD = os.environ.get("ODB_TC_SWIGLU_BWD", "1") != "0"
 TWO_CTA = os.environ.get("ODB_TC_GEMM_2CTA", "1") != "0"     # CTA-pair (cta_group::2, 256x256 tiles) kernels
 
 
@@ -63,6 +66,25 @@ def linear_swiglu(x: torch.Tensor, w_gu: torch.Tensor, gu: torch.Tensor, act: to
     assert x.is_contiguous() and w_gu.is_contiguous() and gu.is_contiguous() and act.is_contiguous()
     _lib.check(_fn("odb_gemm_swiglu", M, I // 128 * 256)(x.data_ptr(), w_gu.data_ptr(), gu.data_ptr(), act.data_ptr(), M, I, K,
                                                _lib.stream_ptr(x)), "gemm_swiglu")
+    _lib.count_launch()
+
+
+def swiglu_bwd_usable(dy: torch.Tensor, w_down_t: torch.Tensor | None, gu: torch.Tensor) -> bool:
+    """The fused down-proj dgrad + SwiGLU backward (CTA-pair kernel only: needs a full wave of 256x256 tiles)."""
+    if not (FUSE_SWIGLU_BWD and TWO_CTA and w_down_t is not None and usable(dy, w_down_t, gu)):
+        return False
+    M, I = dy.shape[0], w_down_t.shape[0]
+    return (I % 64 == 0 and gu.is_contiguous() and gu.shape[1] == 2 * I and ((M + 255) // 256) * ((I + 255) // 256) >= 74
+            and _lib.has_symbol("odb_gemm2_swiglu_bwd"))
+
+
+def linear_swiglu_bwd(dy: torch.Tensor, w_down_t: torch.Tensor, gu: torch.Tensor) -> None:
+    """gu [M, 2I] (gate|up) <- d(gate)|d(up) in place, with d(act) = dy @ w_down_t^T formed in tensor memory only
+    (replaces the down-proj dgrad GEMM + the stand-alone swiglu_bwd kernel: d(act) is neither written nor re-read)."""
+    M, K = dy.shape
+    I = w_down_t.shape[0]
+    _lib.check(_lib.cuda_lib().odb_gemm2_swiglu_bwd(dy.data_ptr(), w_down_t.data_ptr(), gu.data_ptr(), M, I, K, dy.stride(0),
+                                                    w_down_t.stride(0), _lib.stream_ptr(dy)), "gemm_swiglu_bwd")
     _lib.count_launch()
 
 

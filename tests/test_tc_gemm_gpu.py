@@ -92,3 +92,22 @@ def test_wgrad_three_sources_and_views():
     T.wgrad_acc((dq, dk, dv), x, big[:1024])
     ref = torch.cat([dq, dk, dv], 1).double().t() @ x.double()
     assert rel(big[:1024], ref) < 2e-5 and torch.count_nonzero(big[1024:]) == 0
+
+
+@pytest.mark.parametrize("M,I,Kd", [(4096, 2048, 256), (8192, 1280, 768), (5000, 2304, 192), (4096, 2688, 1024)])
+def test_swiglu_backward_epilogue(M, I, Kd):
+    """Down-proj dgrad GEMM with the SwiGLU backward as epilogue == the GEMM followed by the stand-alone kernel."""
+    torch.manual_seed(0)
+    dy = torch.randn(M, Kd, device="cuda").to(BF)
+    w_t = (torch.randn(I, Kd, device="cuda") * 0.1).to(BF)              # down_proj.weight^T: [I, hidden]
+    gu = torch.randn(M, 2 * I, device="cuda").to(BF)
+    assert T.swiglu_bwd_usable(dy, w_t, gu)
+    dact = T.linear(dy, w_t)
+    ref_unfused = K.swiglu_bwd(dact, gu)
+    g, u, d = gu[:, :I].float(), gu[:, I:].float(), dy.float() @ w_t.float().t()
+    sg = torch.sigmoid(g)
+    ref = torch.cat([d * u * sg * (1 + g * (1 - sg)), d * g * sg], dim=1)
+    fused = gu.clone()
+    T.linear_swiglu_bwd(dy, w_t, fused)
+    assert rel(fused, ref) < 6e-3
+    assert rel(fused, ref_unfused) < 2e-3                                # same bf16-rounded d(act), fast-math divide differs
