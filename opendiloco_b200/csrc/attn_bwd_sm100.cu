@@ -32,14 +32,23 @@ namespace attn_bwd {
 
 constexpr int BQ = 128, BKV = 128, D = 64;
 constexpr int TILE = 128 * 128;                  // bytes of a [128 x 64] bf16 tile
-constexpr int THREADS = 512;                   // warp 0 TMA, 1 MMA, 2-3 idle | 4-11 element-wise | 12-15 dQ drain
-constexpr int EW_THREADS = 256, DRAIN_THREADS = 128;
-constexpr int EW_WARP0 = 4, DRAIN_WARP0 = 12;
+// Warp roles: warp 0 TMA, 1 MMA, 2-3 idle | 4 .. 4+4*EWS-1 element-wise | last 4 warps dQ drain.  EWS = threads per key row
+// (2: 64 queries each, 512 threads, registers 96/160/160/96; 4: 32 queries each, 768 threads, registers 64/88x4/64).
+constexpr int DRAIN_THREADS = 128;
+constexpr int EW_WARP0 = 4;
+template <int EWS> struct Roles {
+  static constexpr int EW_WARPS = 4 * EWS, EW_THREADS = 128 * EWS, DRAIN_WARP0 = EW_WARP0 + EW_WARPS;
+  static constexpr int THREADS = 32 * (DRAIN_WARP0 + 4);
+  static constexpr int NQ = 128 / EWS;             // queries (score columns) per element-wise thread
+  static constexpr int DC = 64 / EWS;              // dK / dV columns per thread in the epilogue
+  static constexpr int REG_CTRL = EWS == 2 ? 96 : 64, REG_EW = EWS == 2 ? 160 : 88, REG_DRAIN = EWS == 2 ? 96 : 64;   // must sum to the launch allocation (setmaxnreg trades inside the CTA pool)
+};
 constexpr int QST = 3;                         // Q / dO / stats pipeline stages
 constexpr int STAT_BYTES = 2 * 128 * 4;        // per (b, h, query tile): -lse*log2(e) [128] then -D*scale [128]
 // K, V, QST x (Q, dO), dS^T (2 query chunks), dQ staging fp32 [128 x 64] = 2 chunks of 128 B rows, stats, barriers
 constexpr int SMEM_BYTES = 2 * TILE + 2 * QST * TILE + 2 * TILE + 2 * TILE + QST * STAT_BYTES + 1024 + 256;
 constexpr uint32_t TMEM_COLS = 512;
+constexpr int DEFAULT_EWS = 2;
 
 struct Params {
   int B, S, Hq, Hkv;
@@ -64,10 +73,30 @@ __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.
 template <int N>
 __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
-__global__ void __launch_bounds__(THREADS, 1)
+template <int N>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[N]) {
+  static_assert(N == 16 || N == 32 || N == 64);
+  if constexpr (N == 16) {
+    tmem_ld_32x32b_x16(taddr, r);
+  } else {
+#pragma unroll
+    for (int c = 0; c < N; c += 32) tmem_ld_32x32b_x32(taddr + c, *reinterpret_cast<uint32_t(*)[32]>(&r[c]));
+  }
+}
+template <int N>
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t (&r)[N]) {
+  static_assert(N == 16 || N == 32);
+  if constexpr (N == 16) tmem_st_32x32b_x16(taddr, r);
+  else tmem_st_32x32b_x32(taddr, r);
+}
+
+template <int EWS>
+__global__ void __launch_bounds__(Roles<EWS>::THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                 const __grid_constant__ CUtensorMap tmap_dq, const __grid_constant__ CUtensorMap tmap_dk,
                 const __grid_constant__ CUtensorMap tmap_dv, Params p) {
+  using R = Roles<EWS>;
+  constexpr int EW_THREADS = R::EW_THREADS, DRAIN_WARP0 = R::DRAIN_WARP0, NQ = R::NQ, DC = R::DC;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
@@ -110,11 +139,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     for (int i = 0; i < QST; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
     mbar_init(s_full, 1);
     mbar_init(dp_full, 1);
-    mbar_init(s_free, 8);
-    mbar_init(pds_full, 8);
+    mbar_init(s_free, R::EW_WARPS);
+    mbar_init(pds_full, R::EW_WARPS);
     mbar_init(mma_done, 1);
     mbar_init(dq_empty, 4);
-    mbar_init(dkv_empty, 8);
+    mbar_init(dkv_empty, R::EW_WARPS);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -124,11 +153,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   const uint32_t tb = *tmem_slot;
   const uint32_t tS = tb, tdP = tb + 128, tdV = tb + 256, tdK = tb + 320, tdQ = tb + 384;
 
-  // register file split per warpgroup: 4 x 128 threads x {96, 160, 160, 96} = 64K registers
+  // register file split per warpgroup (EWS = 2: 128 threads x {96, 160, 160, 96}; EWS = 4: 80 at launch -> {64, 88 x 4, 64})
   // (each setmaxnreg sits inside its role branch and the branches only re-join at the final barrier, so ptxas allocates
   // every role's code against its own budget)
   if (warp < EW_WARP0) {
-    reg_dealloc<96>();
+    reg_dealloc<R::REG_CTRL>();
     if (warp == 0 && lane == 0) {
       int st = 0, ph = 0;                                // Q stage ring position / phase
       for (int w = 0; w < nitems; ++w) {
@@ -161,8 +190,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       int st = 0, ph = 0;                                // stage / phase of the NEXT S^T to issue
       // Software pipeline (the tensor pipe executes in issue order):
       //   S^T(it+1) is issued as soon as the element-wise warps hold S^T(it) in registers, so it runs under their math;
-      //   dV/dK(it) follow once P^T/dS^T(it) are in place, dQ(it) once the drain warps emptied the previous dQ tile, and
-      //   dP^T(it+1) goes last because it overwrites the columns P^T/dS^T(it) were read from.
+      //   dV/dK(it) follow once P^T/dS^T(it) are in place, then dP^T(it+1) (it overwrites the columns P^T/dS^T(it) were
+      //   read from), and last dQ(it) once the drain warps emptied the previous dQ tile.
       auto issue_s = [&]() {
         const uint64_t qd = make_smem_desc_sw128(smem_u32(sQ + st * TILE), 16, 1024);
         mbar_wait(&q_full[st], ph);
@@ -209,15 +238,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
           BWD_STAMP(11);
           const bool first = (i == 0);
           if (leader) {
-            // A straight from tensor memory: 16 queries = 8 columns per K step; the two query halves sit 64 columns apart
+            // A straight from tensor memory: 16 queries = 8 columns per K step.  Each element-wise thread's NQ dP^T
+            // columns now hold P^T (first NQ/2) and dS^T (last NQ/2) of its NQ queries.
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              umma_ts(tdV, tdP + (k >> 2) * 64 + (k & 3) * 8, dod + 128 * k, id_ts, (first && k == 0) ? 0u : 1u);
+              umma_ts(tdV, tdP + (16 * k / NQ) * NQ + (16 * k % NQ) / 2, dod + 128 * k, id_ts, (first && k == 0) ? 0u : 1u);
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              umma_ts(tdK, tdP + 32 + (k >> 2) * 64 + (k & 3) * 8, qd + 128 * k, id_ts, (first && k == 0) ? 0u : 1u);
+              umma_ts(tdK, tdP + (16 * k / NQ) * NQ + NQ / 2 + (16 * k % NQ) / 2, qd + 128 * k, id_ts, (first && k == 0) ? 0u : 1u);
           }
           __syncwarp();
+          // dP^T(it+1) only has to wait for dV / dK(it) (they read P^T / dS^T out of its columns); dQ(it) reads dS from
+          // shared memory, so it goes AFTER - the element-wise warps get dP^T(it+1) one GEMM earlier
+          if (i + 1 < iters) issue_dp(nxt);
           if (it > 0) mbar_wait(dq_empty, (it - 1) & 1); // previous dQ tile drained
           tc_fence_after_sync();
           BWD_STAMP(12);
@@ -229,14 +262,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             if (i + 1 == iters) umma_commit(kv_empty);
           }
           __syncwarp();
-          if (i + 1 < iters) issue_dp(nxt);
           cur = nxt;
         }
         g += iters;
       }
     }
   } else if (warp >= DRAIN_WARP0) {
-    reg_dealloc<96>();
+    reg_dealloc<R::REG_DRAIN>();
     // ------------------------------------------------------------------ dQ drain warps
     // dQ tile of iteration `it`: TMEM -> fp32 staging -> TMA reduce-add into the fp32 accumulator, off the critical path
     // of the element-wise warps.
@@ -252,23 +284,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         for (int qi = kb; qi < nq; ++qi, ++it) {
           mbar_wait(mma_done, it & 1);
           tc_fence_after_sync();
-          uint32_t dq[64];
-          tmem_ld_32x32b_x32(tdQ + lane_off, *reinterpret_cast<uint32_t(*)[32]>(&dq[0]));
-          tmem_ld_32x32b_x32(tdQ + lane_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&dq[32]));
-          tmem_ld_wait();
-          tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(dq_empty);
-          BWD_STAMP(6);
           if (elected) tma_store_wait_read<0>();         // previous reduce finished reading the staging tile
           named_bar_sync(3, DRAIN_THREADS);
           BWD_STAMP(7);
 #pragma unroll
-          for (int c = 0; c < 2; ++c)
+          for (int c = 0; c < 2; ++c) {                  // 32 fp32 columns at a time (register budget of this warpgroup)
+            uint32_t dq[32];
+            tmem_ld_32x32b_x32(tdQ + lane_off + c * 32, dq);
+            tmem_ld_wait();
+            if (c == 1) {
+              tc_fence_before_sync();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(dq_empty);
+              BWD_STAMP(6);
+            }
 #pragma unroll
             for (int u = 0; u < 8; ++u)
               *reinterpret_cast<uint4*>(sdQ + c * TILE + row * 128 + ((u ^ (row & 7)) * 16)) =
-                  make_uint4(dq[c * 32 + u * 4 + 0], dq[c * 32 + u * 4 + 1], dq[c * 32 + u * 4 + 2], dq[c * 32 + u * 4 + 3]);
+                  make_uint4(dq[u * 4 + 0], dq[u * 4 + 1], dq[u * 4 + 2], dq[u * 4 + 3]);
+          }
           fence_proxy_async_smem();
           named_bar_sync(4, DRAIN_THREADS);
           if (elected) {
@@ -283,33 +317,32 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     if (elected) tma_store_wait<0>();
   } else {
     // ------------------------------------------------------------------ element-wise warps
-    reg_alloc<160>();
+    reg_alloc<R::REG_EW>();
     const int q = warp & 3;
     const int row = q * 32 + lane;                       // KEY row inside the tile == TMEM lane
-    const int half = (warp - EW_WARP0) >> 2;             // queries [64*half, 64*half + 64) of the query tile
+    const int part = (warp - EW_WARP0) >> 2;             // queries [NQ*part, NQ*part + NQ) of the query tile
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const float c = p.scale_log2;
     const uint64_t c2 = pack2(c, c), sc2 = pack2(p.scale, p.scale);
     const bool elected = threadIdx.x == EW_WARP0 * 32;
     const bool dbg_on = dbg_cta && elected;
-    const uint32_t tPD = tdP + lane_off + half * 64;     // this thread's dP^T columns; P^T -> [0,32), dS^T -> [32,64) of them
+    const uint32_t tPD = tdP + lane_off + part * NQ;     // this thread's dP^T columns; P^T -> first half, dS^T -> second half
     int st = 0, ph = 0;
     for (int w = 0, it = 0; w < nitems; ++w) {
       const int kb = w ? kb_second : kb_first;
       for (int hh = 0; hh < group; ++hh) {
         for (int qi = kb; qi < nq; ++qi, ++it) {
           const bool diag = (qi == kb);
-          const uint32_t stat = smem_u32(sStat + st * 256 + half * 64);
+          const uint32_t stat = smem_u32(sStat + st * 256 + part * NQ);
           BWD_STAMP(0);
           mbar_wait(&q_full[st], ph);                    // the statistics of this query tile are in shared memory
           mbar_wait(s_full, it & 1);
           tc_fence_after_sync();
           BWD_STAMP(1);
-          uint32_t pp[32];
+          uint32_t pp[NQ / 2];
           {
-            uint32_t sr[64];
-            tmem_ld_32x32b_x32(tS + lane_off + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
-            tmem_ld_32x32b_x32(tS + lane_off + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
+            uint32_t sr[NQ];
+            tmem_ld_cols<NQ>(tS + lane_off + part * NQ, sr);
             tmem_ld_wait();
             tc_fence_before_sync();
             __syncwarp();
@@ -317,13 +350,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             BWD_STAMP(2);
             if (diag) {
 #pragma unroll
-              for (int i = 0; i < 64; ++i)
-                if (row > half * 64 + i) sr[i] = 0xff800000u;     // key after query: -inf -> P = 0
+              for (int i = 0; i < NQ; ++i)
+                if (row > part * NQ + i) sr[i] = 0xff800000u;     // key after query: -inf -> P = 0
             }
             // P = exp2(S*c - lse2[query]): packed fp32x2 math; of every four exponentials two go through the MUFU and two
             // through the FMA-pipe polynomial (see attn_sm100.cu).  The per-query statistics are broadcast reads.
 #pragma unroll
-            for (int i = 0; i < 64; i += 4) {
+            for (int i = 0; i < NQ; i += 4) {
               uint64_t nla, nlb;
               lds_2x64(stat + i * 4, nla, nlb);
               const uint64_t ya = ffma2(pack2u(sr[i], sr[i + 1]), c2, nla);
@@ -335,23 +368,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             }
           }
           BWD_STAMP(3);
-          mbar_wait(dp_full, it & 1);                    // dP^T ready; every earlier MMA (dQ of the previous tile) retired
+          mbar_wait(dp_full, it & 1);                    // dP^T ready (dV / dK of the previous tile retired)
           tc_fence_after_sync();
-          uint32_t ds[32];
+          uint32_t ds[NQ / 2];
           {
-            uint32_t dr[64];
-            tmem_ld_32x32b_x32(tPD, *reinterpret_cast<uint32_t(*)[32]>(&dr[0]));
-            tmem_ld_32x32b_x32(tPD + 32, *reinterpret_cast<uint32_t(*)[32]>(&dr[32]));
+            uint32_t dr[NQ];
+            tmem_ld_cols<NQ>(tPD, dr);
             tmem_ld_wait();
             // dS = P * (dP*scale - D*scale): the bracket in packed fp32, the product in packed bf16 (the P the dV GEMM sees)
 #pragma unroll
-            for (int i = 0; i < 64; i += 4) {
+            for (int i = 0; i < NQ; i += 4) {
               uint64_t nda, ndb;
               lds_2x64(stat + 512 + i * 4, nda, ndb);
               ds[i / 2] = mul_bf16x2(pp[i / 2], cvt_bf16x2(ffma2(pack2u(dr[i], dr[i + 1]), sc2, nda)));
               ds[i / 2 + 1] = mul_bf16x2(pp[i / 2 + 1], cvt_bf16x2(ffma2(pack2u(dr[i + 2], dr[i + 3]), sc2, ndb)));
             }
           }
+          if (it > 0) mbar_wait(mma_done, (it - 1) & 1);   // dQ of the previous tile no longer reads the dS buffer
           if (w > 0 && hh == 0 && qi == kb) {
             // the dS buffer doubled as the dK / dV store staging of the previous key tile: its TMA store must have read it
             if (elected) tma_store_wait_read<0>();
@@ -359,12 +392,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
           }
           BWD_STAMP(4);
           // P^T / dS^T -> tensor memory (A operands of dV / dK), dS^T -> shared memory (A operand of dQ, MN-major)
-          tmem_st_32x32b_x32(tPD, pp);
-          tmem_st_32x32b_x32(tPD + 32, ds);
+          tmem_st_cols<NQ / 2>(tPD, pp);
+          tmem_st_cols<NQ / 2>(tPD + NQ / 2, ds);
+          {
+            // query index part*NQ + i sits in 64-query chunk (part*NQ)/64 at 16-byte unit ((part*NQ) % 64) / 8 + u of its key row
+            uint8_t* drow = sdS + ((part * NQ) >> 6) * TILE + row * 128;
+            const int u0 = ((part * NQ) & 63) >> 3;
 #pragma unroll
-          for (int u = 0; u < 8; ++u)
-            *reinterpret_cast<uint4*>(sdS + half * TILE + row * 128 + ((u ^ (row & 7)) * 16)) =
-                make_uint4(ds[u * 4 + 0], ds[u * 4 + 1], ds[u * 4 + 2], ds[u * 4 + 3]);
+            for (int u = 0; u < NQ / 8; ++u)
+              *reinterpret_cast<uint4*>(drow + (((u0 + u) ^ (row & 7)) * 16)) =
+                  make_uint4(ds[u * 4 + 0], ds[u * 4 + 1], ds[u * 4 + 2], ds[u * 4 + 3]);
+          }
           tmem_st_wait();
           fence_proxy_async_smem();
           tc_fence_before_sync();
@@ -377,27 +415,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       // ---- dK / dV epilogue of this key tile: this thread's 32 columns -> bf16 -> staging (the dS buffer) -> TMA store
       mbar_wait(mma_done, (it - 1) & 1);
       tc_fence_after_sync();
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tdK + lane_off + half * 32, r);
+      uint32_t r[DC];
+      tmem_ld_cols<DC>(tdK + lane_off + part * DC, r);
       tmem_ld_wait();
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < DC / 8; ++u) {
         float f[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[u * 8 + i]);
-        *reinterpret_cast<uint4*>(sdS + row * 128 + (((half * 4 + u) ^ (row & 7)) * 16)) = pack8(f);
+        *reinterpret_cast<uint4*>(sdS + row * 128 + (((part * (DC / 8) + u) ^ (row & 7)) * 16)) = pack8(f);
       }
-      tmem_ld_32x32b_x32(tdV + lane_off + half * 32, r);
+      tmem_ld_cols<DC>(tdV + lane_off + part * DC, r);
       tmem_ld_wait();
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(dkv_empty);             // the next key tile may start accumulating
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < DC / 8; ++u) {
         float f[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[u * 8 + i]);
-        *reinterpret_cast<uint4*>(sdS + TILE + row * 128 + (((half * 4 + u) ^ (row & 7)) * 16)) = pack8(f);
+        *reinterpret_cast<uint4*>(sdS + TILE + row * 128 + (((part * (DC / 8) + u) ^ (row & 7)) * 16)) = pack8(f);
       }
       fence_proxy_async_smem();
       named_bar_sync(2, EW_THREADS);
@@ -532,14 +570,17 @@ ODB_EXPORT int odb_attn_bwd(const void* qkv, const void* out, const void* dout, 
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   p.stats = (const float*)stats;
   p.dbg = g_bwd_dbg;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+  static int ews = 0;
+  if (!ews) {
+    const char* env = getenv("ODB_ATTN_BWD_SPLIT");      // element-wise threads per key row: 2 or 4
+    ews = (env && atoi(env) == 2) ? 2 : (env && atoi(env) == 4) ? 4 : DEFAULT_EWS;
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) { ews = 0; return (int)e; }
   }
   dim3 grid((S / BKV + 1) / 2, Hkv, B);
-  attn_bwd_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tq, tdo, tdq, tdk, tdv, p);
+  if (ews == 2) attn_bwd_kernel<2><<<grid, Roles<2>::THREADS, SMEM_BYTES, st>>>(tq, tdo, tdq, tdk, tdv, p);
+  else attn_bwd_kernel<4><<<grid, Roles<4>::THREADS, SMEM_BYTES, st>>>(tq, tdo, tdq, tdk, tdv, p);
   {
     const long long threads = T * (Hq + (cos_t ? Hkv : 0)) * 4;
     attn_bwd_finish_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((const float*)dq_acc, (__nv_bfloat16*)dq,

@@ -199,6 +199,13 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
       ::"r"(taddr), ODB_TMEM_ST_REGS8(r, 0), ODB_TMEM_ST_REGS8(r, 8), ODB_TMEM_ST_REGS8(r, 16), ODB_TMEM_ST_REGS8(r, 24)
       : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), ODB_TMEM_ST_REGS8(r, 0), ODB_TMEM_ST_REGS8(r, 8)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // named barrier among a subset of warps (ids 1..15; 0 is __syncthreads)
