@@ -89,8 +89,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
   // slice, so they share dY / X tiles in L2 and never reduce-add into the same addresses at the same moment
   auto decode = [&](int w, int& m_blk, int& n_blk, int& kb0, int& kb1) {
     const int sp = w / num_tiles, tile = w - sp * num_tiles;
-    m_blk = tile % p.num_m;
-    n_blk = tile / p.num_m;
+    // n fastest: the (few) X-column tiles that share one dY column block run side by side, so a dY slice is fetched from
+    // HBM once even when a token slice has more tiles than the machine has CTA pairs (lm_head: 125 x 4 tiles - with m
+    // fastest its 524 MB dlogits chunk was streamed four times)
+    n_blk = tile % p.num_n;
+    m_blk = tile / p.num_n;
     const int per = (p.kb_total + p.splits - 1) / p.splits;
     kb0 = sp * per;
     kb1 = kb0 + per < p.kb_total ? kb0 + per : p.kb_total;
