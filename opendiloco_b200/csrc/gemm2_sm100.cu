@@ -251,7 +251,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           for (int j = 0; j < 64; ++j) {
             const float gj = bf16_round(g[j]);     // the activation is computed from the bf16 values the backward will see
             const float uj = bf16_round(u[j]);
-            g[j] = __fdividef(gj, 1.f + __expf(-gj)) * uj;
+            g[j] = gj * fast_sigmoid(gj) * uj;
           }
           stage_row_bf16(ba, row, g);
           fence_proxy_async_smem();
@@ -295,7 +295,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const float dj = bf16_round(d[j * 8 + e]);           // the un-fused path rounds d(act) to bf16 first
-              const float sg = __fdividef(1.f, 1.f + __expf(-g[e]));
+              const float sg = fast_sigmoid(g[e]);
               og[e] = dj * u[e] * sg * (1.f + g[e] * (1.f - sg));
               ou[e] = dj * g[e] * sg;
             }

@@ -200,7 +200,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           for (int j = 0; j < 64; ++j) {
             const float gj = bf16_round(g[j]);     // the activation is computed from the bf16 values the backward will see
             const float uj = bf16_round(u[j]);
-            g[j] = __fdividef(gj, 1.f + __expf(-gj)) * uj;
+            g[j] = gj * fast_sigmoid(gj) * uj;
           }
           stage_row_bf16(ba, row, g);
           fence_proxy_async_smem();

@@ -63,3 +63,53 @@ def test_python_loader_and_collation():
     feats[1] = {"input_ids": feats[1]["input_ids"][:5], "attention_mask": [1] * 5}
     batch = collate_causal_lm(feats, pad_token_id=2)
     assert batch["input_ids"].shape == (2, 8) and (batch["labels"][1, 5:] == -100).all() and (batch["attention_mask"][1, 5:] == 0).all()
+
+
+def test_training_utils_fingerprint_schedule_and_inf_probe():
+    """utils/training.py: debug fingerprint (reference utils.py:70-80), cosine schedule (transformers optimization.py:134-140)
+    and the GradScaler inf probe (reference utils.py:124-135)."""
+    import math
+
+    import torch
+
+    from opendiloco_b200.utils.training import (cosine_schedule_with_warmup_lambda, found_inf_grad, get_cosine_schedule_with_warmup,
+                                                hash_tensor_content)
+
+    a = torch.arange(64 * 64, dtype=torch.float32).view(64, 64) / 7.0
+    h = hash_tensor_content(a)
+    assert h == hash_tensor_content(a.clone()) and len(h) == 32
+    b = a.clone()
+    b[40, 40] += 1.0                       # outside the 31 x 31 fingerprint block
+    assert hash_tensor_content(b) == h
+    b[3, 3] += 1.0
+    assert hash_tensor_content(b) != h
+
+    lam = cosine_schedule_with_warmup_lambda(10, 110)
+    assert lam(0) == 0.0 and lam(5) == 0.5 and lam(10) == 1.0
+    assert abs(lam(60) - 0.5) < 1e-12 and lam(110) == 0.0
+    assert abs(lam(210) - 1.0) < 1e-12     # like the HF lambda, the cosine is not clamped past num_training_steps
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.SGD([p], lr=2.0)
+    sched = get_cosine_schedule_with_warmup(opt, 10, 110)
+    lrs = []
+    for _ in range(12):
+        opt.step()
+        sched.step()
+        lrs.append(opt.param_groups[0]["lr"])
+    assert abs(lrs[4] - 1.0) < 1e-12 and abs(lrs[9] - 2.0) < 1e-12
+    assert abs(lrs[11] - 2.0 * 0.5 * (1 + math.cos(math.pi * 2 / 100))) < 1e-12
+
+    class _Scaler:                          # the two attributes found_inf_grad reads
+        def __init__(self, enabled, states):
+            self._enabled, self._per_optimizer_states = enabled, states
+
+        def is_enabled(self):
+            return self._enabled
+
+    assert found_inf_grad(opt, None) is False
+    assert found_inf_grad(opt, _Scaler(False, {})) is False
+    assert found_inf_grad(opt, _Scaler(True, {})) is False
+    ok = {id(opt): {"found_inf_per_device": {"cpu": torch.tensor(0.0)}}}
+    bad = {id(opt): {"found_inf_per_device": {"cpu": torch.tensor(1.0)}}}
+    assert found_inf_grad(opt, _Scaler(True, ok)) is False
+    assert found_inf_grad(opt, _Scaler(True, bad)) is True
