@@ -113,3 +113,32 @@ def test_training_utils_fingerprint_schedule_and_inf_probe():
     bad = {id(opt): {"found_inf_per_device": {"cpu": torch.tensor(1.0)}}}
     assert found_inf_grad(opt, _Scaler(True, ok)) is False
     assert found_inf_grad(opt, _Scaler(True, bad)) is True
+
+
+def test_init_weights_writes_a_loadable_hf_checkpoint(tmp_path):
+    """init_weights CLI (reference open_diloco/init_weights.py:10-25): config.json + model.safetensors with HF names,
+    deterministic in the seed, loadable by this framework and by transformers' LlamaForCausalLM."""
+    import json
+
+    import torch
+
+    from opendiloco_b200.init_weights import main as init_main
+    from opendiloco_b200.models.llama import LlamaForCausalLM
+    from opendiloco_b200.utils.safetensors_io import load_safetensors
+
+    out = tmp_path / "llama-2m-fresh"
+    init_main(["--config-name-or-path", "2m", "--save-to-disk", str(out), "--seed", "3"])
+    cfg = json.loads((out / "config.json").read_text())
+    assert cfg["hidden_size"] == 64 and cfg["num_hidden_layers"] == 2
+    sd = load_safetensors(str(out / "model.safetensors"))
+    assert "model.embed_tokens.weight" in sd and "lm_head.weight" in sd and "model.layers.1.mlp.down_proj.weight" in sd
+    m1 = LlamaForCausalLM.from_pretrained(str(out), device="cpu", precision="32-true")
+    m2 = LlamaForCausalLM(m1.config, device="cpu", precision="32-true", seed=3)
+    assert torch.equal(m1.arena.master, m2.arena.master)
+    transformers = pytest.importorskip("transformers")
+    hf = transformers.LlamaForCausalLM.from_pretrained(str(out), torch_dtype=torch.float32)
+    ids = torch.randint(0, m1.config.vocab_size, (2, 16))
+    with torch.no_grad():
+        ref = hf(input_ids=ids, labels=ids).loss
+        ours = m1(input_ids=ids, labels=ids).loss
+    assert abs(float(ref) - float(ours)) < 1e-4
