@@ -65,7 +65,7 @@ class DiloCoProgressTracker:
     def __init__(self, batch_size: int, num_inner_steps: int, *, dht: DHT | None = None, prefix: str = "diloco",
                  target_batch_size: int | None = None, min_refresh_period: float = 0.5, max_refresh_period: float = 2.0,
                  default_refresh_period: float = 1.0, performance_ema_alpha: float = 0.1, publish: bool = False,
-                 **_ignored):
+                 peer_ttl: float | None = None, **_ignored):
         self.batch_size, self.num_inner_steps = batch_size, num_inner_steps
         self.dht, self.prefix = dht, prefix
         self.target_batch_size = target_batch_size if target_batch_size is not None else batch_size * num_inner_steps
@@ -76,6 +76,10 @@ class DiloCoProgressTracker:
         self._global_epoch_hint = 0
         self._paused = False
         self._publish = publish
+        # a peer whose last record is older than this many seconds no longer counts as alive (the reference's DHT records
+        # carry an expiration time for the same purpose: hivemind ProgressTracker, metadata_expiration); a worker that
+        # died therefore shows up as num_peers < galaxy_size -> "Lost a diloco worker" (train_fsdp.py:440-446)
+        self.peer_ttl = float(os.environ.get("ODB_PEER_TTL", 120.0)) if peer_ttl is None else float(peer_ttl)
         self.global_progress = self._make_global()
 
     # -- reference properties ------------------------------------------------------------------
@@ -127,9 +131,12 @@ class DiloCoProgressTracker:
         self.local_progress.samples_accumulated = samples_accumulated
         self.local_progress.samples_per_second = self.performance_ema.samples_per_second
         self.local_progress.time = get_dht_time()
+        fetch_due = self._publish and get_dht_time() >= self.global_progress.next_fetch_time
         self.global_progress = self._make_global()
         if self._publish:
             self._publish_progress()
+            if fetch_due:                     # hivemind refreshes the swarm view in a background thread at this cadence
+                self.fetch_global_progress()
 
     def update_epoch(self, new_epoch: int | None = None) -> int:
         if new_epoch is None:
@@ -172,9 +179,11 @@ class DiloCoProgressTracker:
             try:
                 if not store.check([f"{self.prefix}_progress/{pid}"]):
                     continue
-                e, s, sps, _t = store.get(f"{self.prefix}_progress/{pid}").decode().split(",")
+                e, s, sps, t_rec = store.get(f"{self.prefix}_progress/{pid}").decode().split(",")
             except Exception:
                 continue
+            if pid != self.local_progress.peer_id and now - float(t_rec) > self.peer_ttl:
+                continue                      # stale record: the peer stopped reporting
             alive += 1
             epoch = max(epoch, int(e))
             if int(e) >= epoch:

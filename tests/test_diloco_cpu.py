@@ -156,3 +156,42 @@ def test_multi_worker_equivalence_gloo():
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "FAIL" not in res.stdout and res.stdout.count("OK") >= 7
+
+
+def test_progress_tracker_drops_stale_peers():
+    """Peers publish (epoch, samples, samples/s, time) records; one whose record is older than ``peer_ttl`` stops counting
+    as alive, which is how a dead worker becomes visible as num_peers < galaxy_size (train_fsdp.py:440-446)."""
+    import time
+
+    class _Store(dict):
+        def set(self, k, v):
+            self[k] = v.encode() if isinstance(v, str) else v
+
+        def get(self, k):
+            return self[k]
+
+        def check(self, keys):
+            return all(k in self for k in keys)
+
+    class _DHT:
+        def __init__(self, store, me, n):
+            self._s, self.peer_id, self.num_peers = store, f"worker-{me}", n
+
+        def store(self):
+            return self._s
+
+        def peer_ids(self):
+            return [f"worker-{r}" for r in range(self.num_peers)]
+
+    store = _Store()
+    a = DiloCoProgressTracker(batch_size=4, num_inner_steps=10, dht=_DHT(store, 0, 3), publish=True, peer_ttl=0.3)
+    b = DiloCoProgressTracker(batch_size=4, num_inner_steps=10, dht=_DHT(store, 1, 3), publish=True, peer_ttl=0.3)
+    a.report_local_progress(0, 8)
+    b.report_local_progress(2, 4)
+    g = a.fetch_global_progress()
+    assert g.num_peers == 2 and g.epoch == 2 and a.global_epoch == 2 and a.ready_to_update_epoch      # worker-2 never reported
+    time.sleep(0.4)
+    a.report_local_progress(0, 12)           # a keeps reporting, b went silent
+    assert a.fetch_global_progress().num_peers == 1
+    b.report_local_progress(2, 8)            # b is back
+    assert a.fetch_global_progress().num_peers == 2
