@@ -38,6 +38,19 @@ class DHT:
             group = dist.group.WORLD
         self.group = group
         self._alive = bool(start)
+        # Optional native membership board (csrc/host/rendezvous.cc): an ``odb://host:port`` entry in ``initial_peers`` (or
+        # ODB_BOARD) makes progress records, arrival handshakes and liveness go through it instead of the c10d store -
+        # it outlives / spans torchrun jobs and is visible to launchers and monitors.
+        self.board = None
+        board_addr = next((p for p in self.initial_peers if str(p).startswith("odb://")), os.environ.get("ODB_BOARD"))
+        if start and board_addr:
+            from . import rendezvous as rdv
+
+            hp = rdv.parse_address(str(board_addr))
+            if hp is None:
+                raise ValueError(f"bad board address {board_addr!r} (expected odb://host:port)")
+            self.board = rdv.RendezvousClient(hp[0], hp[1], peer_id=self.peer_id)
+            self.board.start_heartbeat(ttl=float(os.environ.get("ODB_PEER_TTL", 120.0)))
 
     # -- membership
     @property
@@ -55,7 +68,13 @@ class DHT:
     def peer_ids(self) -> list[str]:
         return [f"worker-{r}" for r in range(self.num_peers)]
 
+    def alive_peers(self) -> list[str]:
+        """Peers with a live heartbeat on the board (all peers of the group when no board is attached)."""
+        return sorted(self.board.alive_peers()) if self.board is not None else self.peer_ids()
+
     def store(self):
+        if self.board is not None:
+            return self.board.as_store()
         if not dist.is_initialized():
             return None
         try:
@@ -77,6 +96,9 @@ class DHT:
 
     def shutdown(self) -> None:
         self._alive = False
+        if self.board is not None:
+            self.board.close()
+            self.board = None
 
 
 def log_visible_maddrs(maddrs, only_p2p: bool = False) -> None:

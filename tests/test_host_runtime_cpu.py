@@ -142,3 +142,88 @@ def test_init_weights_writes_a_loadable_hf_checkpoint(tmp_path):
         ref = hf(input_ids=ids, labels=ids).loss
         ours = m1(input_ids=ids, labels=ids).loss
     assert abs(float(ref) - float(ours)) < 1e-4
+
+
+@needs_host
+def test_native_rendezvous_board():
+    """csrc/host/rendezvous.cc: key-value records, atomic counters, prefix counts, heartbeats with expiry, the store
+    adapter the progress tracker uses - two clients against one in-process server."""
+    import threading
+    import time
+
+    from opendiloco_b200.parallel import rendezvous as rdv
+
+    assert rdv.available()
+    assert rdv.parse_address("odb://127.0.0.1:29400") == ("127.0.0.1", 29400) and rdv.parse_address("/ip4/1.2.3.4") is None
+    server = rdv.RendezvousServer(0)
+    a = rdv.RendezvousClient("127.0.0.1", server.port, peer_id="worker-0")
+    b = rdv.RendezvousClient("127.0.0.1", server.port, peer_id="worker-1")
+    try:
+        a.set("diloco_progress/worker-0", "3,128,55.5,1.0")
+        assert b.get("diloco_progress/worker-0") == b"3,128,55.5,1.0" and b.get("missing") is None
+        big = bytes(range(256)) * 64                          # larger than the first receive buffer
+        a.set("blob", big)
+        assert b.get("blob") == big
+        # arrival counter of an outer step, hammered from two threads
+        def bump(c):
+            for _ in range(200):
+                c.add("arrive/7", 1)
+        ts = [threading.Thread(target=bump, args=(c,)) for c in (a, b)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert a.add("arrive/7", 0) == 400
+        a.set("run/arrive/0/0", "1")
+        b.set("run/arrive/0/1", "1")
+        assert a.count("run/arrive/0/") == 2 and a.wait(["run/arrive/0/0", "run/arrive/0/1"], 1.0)
+        assert not a.wait(["run/arrive/1/0"], 0.05)
+        assert b.delete("run/arrive/0/1") and not b.delete("run/arrive/0/1") and a.count("run/arrive/0/") == 1
+        # liveness: b beats once with a short ttl and expires, a keeps a background heartbeat
+        a.start_heartbeat(ttl=0.6, period=0.1)
+        b.heartbeat(ttl=0.15)
+        assert sorted(a.alive_peers()) == ["worker-0", "worker-1"]
+        time.sleep(0.3)
+        assert a.alive_peers() == ["worker-0"]
+        # the store adapter drives the progress tracker
+        from opendiloco_b200.parallel.diloco import DiloCoProgressTracker
+
+        class _DHT:
+            def __init__(self, store, me):
+                self._s, self.peer_id, self.num_peers = store, f"worker-{me}", 2
+
+            def store(self):
+                return self._s
+
+            def peer_ids(self):
+                return ["worker-0", "worker-1"]
+
+        ta = DiloCoProgressTracker(batch_size=4, num_inner_steps=10, dht=_DHT(a.as_store(), 0), publish=True)
+        tb = DiloCoProgressTracker(batch_size=4, num_inner_steps=10, dht=_DHT(b.as_store(), 1), publish=True)
+        ta.report_local_progress(0, 8)
+        tb.report_local_progress(1, 4)
+        g = ta.fetch_global_progress()
+        assert g.num_peers == 2 and g.epoch == 1
+        assert server.num_keys() >= 4
+    finally:
+        a.close()
+        b.close()
+        server.stop()
+
+
+@needs_host
+def test_dht_uses_the_native_board_when_given_an_odb_address():
+    from opendiloco_b200.parallel import rendezvous as rdv
+    from opendiloco_b200.parallel.swarm import DHT
+
+    server = rdv.RendezvousServer(0)
+    try:
+        dht = DHT(start=True, initial_peers=[f"odb://127.0.0.1:{server.port}"])
+        assert dht.board is not None and dht.alive_peers() == ["worker-0"]
+        st = dht.store()
+        st.set("k", "v")
+        assert st.get("k") == b"v" and st.check(["k"]) and not st.check(["k", "nope"]) and st.add("n", 2) == 2
+        dht.shutdown()
+        assert dht.board is None
+        plain = DHT(start=True)
+        assert plain.board is None and plain.alive_peers() == ["worker-0"]
+    finally:
+        server.stop()
