@@ -84,9 +84,11 @@ class _Workspace:
 
 
 class LlamaEngine:
-    def __init__(self, cfg: LlamaConfig, arena: ParamArena, lce_chunk: int = 8192):
+    def __init__(self, cfg: LlamaConfig, arena: ParamArena, lce_chunk: int = 32768):
         self.cfg, self.arena = cfg, arena
-        self.lce_chunk = lce_chunk
+        # rows of the logits tile of the chunked linear-cross-entropy (ODB_LCE_CHUNK overrides: larger = fewer, fuller GEMM
+        # launches and less reduce-add traffic into the lm_head gradient, at 64 KB of bf16 logits per row)
+        self.lce_chunk = int(os.environ.get("ODB_LCE_CHUNK", lce_chunk))
         self._ws: dict[tuple, _Workspace] = {}
         self.collect_act_norms = False
         self.act_norms: dict[str, torch.Tensor] = {}
@@ -370,7 +372,7 @@ class LlamaForCausalLM(nn.Module):
     """Drop-in for the HF class the reference trains (train_fsdp.py:171-174, train_diloco_torch.py:183)."""
 
     def __init__(self, config: LlamaConfig, device=None, precision: str = "bf16-mixed", seed: int | None = None,
-                 init: bool = True, lce_chunk: int = 8192):
+                 init: bool = True, lce_chunk: int = 32768):
         super().__init__()
         self.config = config
         self.precision = precision
