@@ -124,6 +124,75 @@ def all_reduce_avg_(buf: torch.Tensor, group) -> torch.Tensor:
     return buf
 
 
+def _global_rank(group, r: int) -> int:
+    return r if (group is None or group is dist.group.WORLD) else dist.get_global_rank(group, r)
+
+
+def p2p_all_reduce_mean_(buf: torch.Tensor, members: list[int], group) -> torch.Tensor:
+    """In-place mean of ONE flat buffer over a SUBSET of the group (``members`` = sorted ranks inside ``group``), built
+    from point-to-point transfers only, so ranks outside the subset do not have to take part - the elastic (NO_WAIT)
+    outer round.  Butterfly: member j owns slice j; everybody sends slice j to its owner, the owner averages and sends
+    the result back to everybody (2 * (k-1)/k of the vector per member, like a reduce-scatter + all-gather)."""
+    k = len(members)
+    if k <= 1:
+        return buf
+    me = dist.get_rank(group)
+    idx = members.index(me)
+    flat = buf.view(-1)
+    n = flat.numel()
+    per = -(-n // k)
+    per += (-per) % 8                                    # keep slices 8-element aligned
+    bounds = [(min(j * per, n), min((j + 1) * per, n)) for j in range(k)]
+    lo, hi = bounds[idx]
+    mine = flat[lo:hi]
+    # phase 1: my slice of everybody's vector comes to me
+    inbox = [torch.empty_like(mine) for _ in range(k - 1)]
+    ops, slot = [], 0
+    for j, r in enumerate(members):
+        if j == idx:
+            continue
+        a, b = bounds[j]
+        if b > a:
+            ops.append(dist.P2POp(dist.isend, flat[a:b], _global_rank(group, r), group))
+        if hi > lo:
+            ops.append(dist.P2POp(dist.irecv, inbox[slot], _global_rank(group, r), group))
+        slot += 1
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    if hi > lo:
+        acc = mine.float() if mine.dtype not in (torch.float32, torch.float64) else mine
+        for t in inbox:
+            acc += t.to(acc.dtype)
+        acc /= k
+        if acc is not mine:
+            mine.copy_(acc)
+    # phase 2: averaged slices go back out
+    ops = []
+    for j, r in enumerate(members):
+        if j == idx:
+            continue
+        a, b = bounds[j]
+        if hi > lo:
+            ops.append(dist.P2POp(dist.isend, mine, _global_rank(group, r), group))
+        if b > a:
+            ops.append(dist.P2POp(dist.irecv, flat[a:b], _global_rank(group, r), group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return buf
+
+
+def p2p_send_(bufs: list[torch.Tensor], dst_rank_in_group: int, group) -> None:
+    for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, b, _global_rank(group, dst_rank_in_group), group) for b in bufs]):
+        req.wait()
+
+
+def p2p_recv_(bufs: list[torch.Tensor], src_rank_in_group: int, group) -> None:
+    for req in dist.batch_isend_irecv([dist.P2POp(dist.irecv, b, _global_rank(group, src_rank_in_group), group) for b in bufs]):
+        req.wait()
+
+
 def all_reduce_sum_(buf: torch.Tensor, group) -> torch.Tensor:
     if group_size(group) > 1:
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)

@@ -267,11 +267,26 @@ class DiLoCoGradAverager:
             g.copy_(opt_p.data - main_p.detach().to(opt_p.device), non_blocking=True)
 
     @torch.no_grad()
-    def _all_reduce(self) -> None:
+    def _all_reduce(self, members: list[int] | None = None) -> None:
         group = self.group
         if comm.group_size(group) <= 1:
             return
         t0 = time.perf_counter()
+        if members is not None and len(members) < comm.group_size(group):
+            # elastic round (NO_WAIT): only the peers that formed this round exchange data, point to point
+            if self._flat is not None:
+                comm.p2p_all_reduce_mean_(self._flat[1], members, group)
+            else:
+                grads = list(self._averaged_grads)
+                dev = comm_device(group, grads[0].device)
+                flat = torch.cat([g.reshape(-1).to(dev, torch.float32) for g in grads])
+                comm.p2p_all_reduce_mean_(flat, members, group)
+                off = 0
+                for g in grads:
+                    g.copy_(flat[off:off + g.numel()].view_as(g))
+                    off += g.numel()
+            self.last_allreduce_seconds = time.perf_counter() - t0
+            return
         if self._flat is not None:
             buf = self._flat[1]
             if self.compression is not None and not self.compression.is_identity:
@@ -294,19 +309,24 @@ class DiLoCoGradAverager:
                 off += g.numel()
         self.last_allreduce_seconds = time.perf_counter() - t0
 
-    def step(self, control: StepControl | None = None, timeout: float | None = None, wait: bool = True, **kwargs):
+    def step(self, control: StepControl | None = None, timeout: float | None = None, wait: bool = True,
+             members: list[int] | None = None, **kwargs):
         """Compute the pseudo-gradient, average it with the peers, leave the mean in the outer grads
         (hivemind_diloco.py:134-156).  Returns {peer_id: None} for every member of the round (or the control if
-        ``wait=False``; the collective itself is stream-ordered, nothing runs on a background thread)."""
+        ``wait=False``; the collective itself is stream-ordered, nothing runs on a background thread).
+        ``members``: ranks (in the outer group) that formed this round; None = everybody."""
         if control is None:
             control = self.schedule_step(timeout=timeout, **kwargs)
         self.compute_and_load_pseudo_grad_into_averager()
         control.allow_allreduce()
         try:
-            self._all_reduce()
+            self._all_reduce(members)
             self._new_averaged_grads = True
-            members = self.dht.peer_ids() if self.dht is not None else [self.peer_id]
-            control.set_result({pid: None for pid in members})
+            if members is not None:
+                ids = [f"worker-{r}" for r in members]
+            else:
+                ids = self.dht.peer_ids() if self.dht is not None else [self.peer_id]
+            control.set_result({pid: None for pid in ids})
         except BaseException as e:  # surfaced through control.result(), like an MPFuture
             control.set_exception(e)
         return control.result(timeout) if wait else control
@@ -403,7 +423,7 @@ class DiLoCoStateAverager:
     # -- the outer step ---------------------------------------------------------------------------------
     @torch.no_grad()
     def step(self, *, increment_epoch: bool = True, optimizer_step: bool = True, averaging_round: bool = False,
-             zero_grad: bool = False, fused_solo: bool = False, **_ignored) -> None:
+             zero_grad: bool = False, fused_solo: bool = False, members: list[int] | None = None, **_ignored) -> None:
         """Outer optimizer step on theta_outer using the (already averaged) pseudo-gradient in its .grad buffers, then
         theta_local <- theta_outer.  ``fused_solo``: single-worker form, delta computed inside the kernel."""
         if optimizer_step:
@@ -419,7 +439,7 @@ class DiLoCoStateAverager:
                 self.optimizer.step()
                 self.apply_optimizer_parameters()
         if averaging_round and comm.group_size(self.dht.group if self.dht else None) > 1:
-            self.average_state()
+            self.average_state(members)
         if zero_grad:
             self.delta.zero_()
         if increment_epoch:
@@ -437,9 +457,17 @@ class DiLoCoStateAverager:
         self.fv.gather_compute_weights()
 
     @torch.no_grad()
-    def average_state(self) -> None:
-        """Parameter (+momentum) averaging round - the drift-repair path (reference H2, hivemind_diloco.py:654-665)."""
+    def average_state(self, members: list[int] | None = None) -> None:
+        """Parameter (+momentum) averaging round - the drift-repair path (reference H2, hivemind_diloco.py:654-665).
+        ``members``: restrict it to the peers of an elastic round (point-to-point transfers)."""
         group = self.dht.group if self.dht else None
+        if members is not None and len(members) < comm.group_size(group):
+            if len(members) > 1:
+                comm.p2p_all_reduce_mean_(self.theta_outer, members, group)
+                if self.momentum_buffer is not None:
+                    comm.p2p_all_reduce_mean_(self.momentum_buffer, members, group)
+                self.apply_optimizer_parameters()
+            return
         comm.all_reduce_avg_(self.theta_outer, group)
         if self.momentum_buffer is not None:
             comm.all_reduce_avg_(self.momentum_buffer, group)
@@ -605,8 +633,12 @@ class DiLoCoOptimizer:
                 loss = closure()
         if self._should_load_state_from_peers():
             logger.log(self.status_loglevel, "Peer is out of sync")
-            self.load_state_from_peers()
-            return loss
+            if self.all_reduce_strategy == AllReduceStrategy.NO_WAIT:
+                if self._resync_from_swarm():       # point-to-point download served by the next round's leader
+                    return loss
+            else:
+                self.load_state_from_peers()
+                return loss
         self.tracker.report_local_progress(self.local_epoch, self.tracker.local_progress.samples_accumulated + batch_size)
         self._maybe_schedule_gradient_averaging()
         if scaler is not None:
@@ -677,22 +709,148 @@ class DiLoCoOptimizer:
         logger.log(self.status_loglevel, f"Timeout waiting for peers, going to skip slowest peers; present={present}")
         return present
 
+    # ------------------------------------------------------------------------------------------ elastic rounds (NO_WAIT)
+    def _form_round(self) -> tuple[list[int], bool] | None:
+        """NO_WAIT matchmaking through the membership board (hivemind: the fastest peer triggers the round and whoever
+        shows up within ``matchmaking_time`` joins it; the others form the next round among themselves).  The first
+        arrival of round r of this epoch is its leader: it waits ``matchmaking_time`` (or until nobody else can come),
+        publishes the member list and everybody listed averages with point-to-point transfers - ranks that are still
+        training are not needed.  Returns (sorted member ranks, am_i_leader), or None when there is no board."""
+        store = self.dht.store() if self.dht is not None else None
+        n = self.num_peers
+        if store is None or n <= 1:
+            return None
+        epoch, me = self.local_epoch, self.dht.rank_in_group
+        inject = os.environ.get("ODB_FAULT_INJECT")      # "rank:epoch[:seconds]" - that worker arrives late
+        if inject:
+            f = inject.split(":")
+            if int(f[0]) == me and int(f[1]) == epoch:
+                delay = float(f[2]) if len(f) > 2 else 1e9
+                logger.warning(f"fault injection: worker {me} stalls {delay:.1f}s before outer step {epoch}")
+                time.sleep(min(delay, 3600.0))
+        base = f"{self.run_id}/round/{epoch}"
+        done_before = 0                                  # peers that already finished this epoch in earlier rounds
+        r = 0
+        while True:
+            mkey = f"{base}/{r}/members"
+            if store.check([mkey]):                      # round r is closed: try the next one
+                done_before += len(store.get(mkey).decode().split(","))
+                r += 1
+                continue
+            order = int(store.add(f"{base}/{r}/count", 1))
+            store.set(f"{base}/{r}/arrive/{me}", "1")
+            keys = [f"{base}/{r}/arrive/{q}" for q in range(n)]
+            if order == 1:
+                deadline = time.perf_counter() + float(self.matchmaking_time)
+                while time.perf_counter() < deadline:
+                    if sum(store.check([k]) for k in keys) >= n - done_before:
+                        break
+                    time.sleep(0.001)
+                members = [q for q in range(n) if store.check([keys[q]])]
+                store.set(mkey, ",".join(str(q) for q in members))
+                return members, True
+            deadline = time.perf_counter() + float(self.matchmaking_time) + float(self.averaging_timeout or 60.0)
+            while not store.check([mkey]):
+                if time.perf_counter() > deadline:
+                    raise TimeoutError(f"round {r} of outer step {epoch}: the leader never published the member list")
+                time.sleep(0.001)
+            members = [int(q) for q in store.get(mkey).decode().split(",")]
+            if me in members:
+                return members, False
+            done_before += len(members)                  # my arrival raced with the leader's snapshot: next round
+            r += 1
+
+    def _serve_resync_requests(self) -> None:
+        """Round leader, after its outer update: hand theta_outer / momentum / epoch to peers that fell behind and asked
+        for the swarm state (the reference's load_state_from_peers, served between two rounds instead of by a
+        background thread)."""
+        store = self.dht.store() if self.dht is not None else None
+        if store is None:
+            return
+        sa, me = self.state_averager, self.dht.rank_in_group
+        for q in range(self.num_peers):
+            rkey = f"{self.run_id}/resync/request/{q}"
+            if q == me or not store.check([rkey]):
+                continue
+            req = store.get(rkey).decode()
+            if req == "" or int(store.add(f"{self.run_id}/resync/claim/{q}/{req}", 1)) != 1:
+                continue                                 # nothing pending, or another leader serves it
+            logger.log(self.status_loglevel, f"serving swarm state (epoch {self.local_epoch}) to worker {q}")
+            store.set(f"{self.run_id}/resync/grant/{q}/{req}", f"{me},{self.local_epoch}")
+            bufs = [sa.theta_outer] + ([sa.momentum_buffer] if sa.momentum_buffer is not None else [])
+            comm.p2p_send_(bufs, q, self.dht.group)
+
+    def _resync_from_swarm(self) -> bool:
+        """Lagging peer: ask for the swarm state on the board and block until a round leader sends it."""
+        store = self.dht.store() if self.dht is not None else None
+        if store is None:
+            return False
+        sa, me = self.state_averager, self.dht.rank_in_group
+        self._resync_seq = getattr(self, "_resync_seq", 0) + 1
+        req = str(self._resync_seq)
+        store.set(f"{self.run_id}/resync/request/{me}", req)
+        gkey = f"{self.run_id}/resync/grant/{me}/{req}"
+        deadline = time.perf_counter() + float(self.averaging_timeout or 600.0)
+        while not store.check([gkey]):
+            if time.perf_counter() > deadline:
+                store.set(f"{self.run_id}/resync/request/{me}", "")
+                logger.warning("no round leader served the state request in time; continuing with the local state")
+                return False
+            time.sleep(0.005)
+        src, epoch = (int(x) for x in store.get(gkey).decode().split(","))
+        store.set(f"{self.run_id}/resync/request/{me}", "")
+        with self.tracker.pause_updates():
+            bufs = [sa.theta_outer] + ([sa.momentum_buffer] if sa.momentum_buffer is not None else [])
+            comm.p2p_recv_(bufs, src, self.dht.group)
+            sa.local_epoch = epoch
+            sa.apply_optimizer_parameters()
+            self.tracker.update_epoch(epoch)
+            self.tracker.report_local_progress(epoch, samples_accumulated=0)
+        logger.log(self.status_loglevel, f"adopted the swarm state of worker {src} at epoch {epoch}")
+        return True
+
     def _update_global_epoch(self) -> None:
         """The outer step (hivemind_diloco.py:570-679)."""
         assert self._schema_hash == self._compute_schema_hash(), "parameters changed during iteration"
         t_start = time.perf_counter()
         sa, ga = self.state_averager, self.diloco_grad_averager
-        present = self._wait_for_peers() if self.num_peers > 1 else None
-        if present is not None and len(present) < self.num_peers:
-            raise RuntimeError(
-                f"DiLoCo worker(s) missing at outer step {self.local_epoch}: present ranks {present} of {self.num_peers}. "
-                "Static NVLink groups cannot shrink mid-collective; restart from the last checkpoint "
-                "(--hv.fail_rank_drop semantics, train_fsdp.py:452-457).")
+        members, leader = None, False
+        if self.num_peers > 1 and self.all_reduce_strategy == AllReduceStrategy.NO_WAIT:
+            formed = self._form_round()
+            if formed is not None:
+                members, leader = formed
+                if len(members) == self.num_peers:
+                    members = None                       # everybody made it: the ordinary full-group round
+                else:
+                    logger.log(self.status_loglevel, f"outer step {self.local_epoch}: elastic round with workers {members} "
+                                                     f"of {self.num_peers}")
+        elif self.num_peers > 1:
+            present = self._wait_for_peers()
+            if present is not None and len(present) < self.num_peers:
+                raise RuntimeError(
+                    f"DiLoCo worker(s) missing at outer step {self.local_epoch}: present ranks {present} of {self.num_peers}. "
+                    "WAIT_FOR_ALL rounds need every worker; restart from the last checkpoint (--hv.fail_rank_drop "
+                    "semantics, train_fsdp.py:452-457) or use AllReduceStrategy.NO_WAIT for elastic rounds.")
+        self.last_round_members = members if members is not None else list(range(self.num_peers))
         with self.tracker.pause_updates():
-            next_epoch = max(self.local_epoch + 1, self.tracker.global_epoch)
+            next_epoch = max(self.local_epoch + 1, self.tracker.global_epoch) if members is None else self.local_epoch + 1
             average_state = (self.num_peers > 1 and self.average_state_every > 0
                              and next_epoch % self.average_state_every == 0)
-            if self._fused is not None:
+            if members is not None:
+                self._drifted = True                     # the swarm split this epoch: theta_outer differs between rounds
+            elif getattr(self, "_drifted", False) and self.num_peers > 1:
+                # first full round after a split epoch (every worker saw the split): repair the drift by averaging
+                # theta_outer / momentum over everybody, what hivemind's state averaging does every epoch
+                average_state, self._drifted = True, False
+            if members is not None and len(members) == 1:
+                # nobody else showed up in time: this worker's own pseudo-gradient is the round
+                sa.step(increment_epoch=True, optimizer_step=True, averaging_round=False, fused_solo=True)
+            elif members is not None:
+                ga.step(wait=True, timeout=self.averaging_timeout, control=self.scheduled_diloco_grads, members=members)
+                ga.notify_used_averaged_gradients()
+                self.scheduled_diloco_grads = None
+                sa.step(increment_epoch=True, optimizer_step=True, averaging_round=average_state, members=members)
+            elif self._fused is not None:
                 self._fused.outer_step()                    # pseudo-grad + NVLink reduce + Nesterov in ONE kernel
                 sa.step(increment_epoch=True, optimizer_step=False, averaging_round=average_state)
             elif self.num_peers > 1:
@@ -704,6 +862,8 @@ class DiLoCoOptimizer:
                 sa.step(increment_epoch=True, optimizer_step=True, averaging_round=average_state)
             else:
                 sa.step(increment_epoch=True, optimizer_step=True, averaging_round=False, fused_solo=True)
+            if leader:
+                self._serve_resync_requests()
             if self.scheduled_state is not None and not self.scheduled_state.done():
                 self.scheduled_state.cancel()
             self.scheduled_state = None
