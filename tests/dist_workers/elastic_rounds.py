@@ -33,6 +33,16 @@ def check(name, cond):
     print(f"[rank {rank}] {name}: {'OK' if cond else 'FAIL'}", flush=True)
 
 
+# the subset butterfly itself: ranks 0 and 2 average a 1003-element vector (uneven slices), rank 1 is not involved
+if rank in (0, 2):
+    v = torch.arange(1003, dtype=torch.float32) * (rank + 1)
+    comm.p2p_all_reduce_mean_(v, [0, 2], dist.group.WORLD)
+    check("p2p subset mean", torch.allclose(v, torch.arange(1003, dtype=torch.float32) * 2.0))
+    w = torch.full((5,), float(rank), dtype=torch.bfloat16)          # fewer elements than members x 8: empty slices
+    comm.p2p_all_reduce_mean_(w, [0, 2], dist.group.WORLD)
+    check("p2p subset mean, tiny bf16", torch.allclose(w.float(), torch.full((5,), 1.0)))
+
+
 def inner_steps(scale):
     """H plain-SGD steps with gradient = scale  =>  theta_local moves by -H * scale."""
     for _ in range(H):
