@@ -227,3 +227,30 @@ def test_dht_uses_the_native_board_when_given_an_odb_address():
         assert plain.board is None and plain.alive_peers() == ["worker-0"]
     finally:
         server.stop()
+
+
+def test_cli_flag_grammar_matches_the_reference_launch_lines():
+    """utils/config.py: the flag grammar of the reference's README commands (pydantic_config / cyclopts)
+    and the strictness of the config models."""
+    from opendiloco_b200.train_fsdp import Config
+    from opendiloco_b200.utils.config import parse_argv
+
+    argv = ("--per-device-train-batch-size 16 --total_batch_size=2048 --total-steps 88_000 --lr 4e-4 --path-model 1b --fake-data "
+            "--no-torch-compile --sharding-strategy _HYBRID_SHARD_ZERO2 --hv.local-steps 500 --hv.galaxy-size 4 --hv.world-rank 1 "
+            "--hv.initial-peers tcp://127.0.0.1:29400 --hv.skip-load-from-peers --ckpt.interval 8000 --ckpt.resume true "
+            "--max-steps -1").split()
+    raw = parse_argv(argv)
+    assert raw["per_device_train_batch_size"] == "16" and raw["total_batch_size"] == "2048" and raw["total_steps"] == "88000"
+    assert raw["fake_data"] is True and raw["torch_compile"] is False and raw["max_steps"] == "-1"
+    assert raw["hv"] == {"local_steps": "500", "galaxy_size": "4", "world_rank": "1", "initial_peers": "tcp://127.0.0.1:29400",
+                         "skip_load_from_peers": True}
+    assert raw["ckpt"] == {"interval": "8000", "resume": True}
+    cfg = Config(**{k: v for k, v in raw.items() if k != "max_steps"})
+    assert cfg.total_steps == 88000 and cfg.lr == 4e-4 and cfg.hv.local_steps == 500 and cfg.hv.galaxy_size == 4
+    assert cfg.sharding_strategy == "_HYBRID_SHARD_ZERO2" and cfg.torch_compile is False and cfg.ckpt.interval == 8000
+    with pytest.raises(Exception):
+        Config(**parse_argv(["--path-model", "2m", "--not-a-flag", "1"]))          # unknown flags are errors
+    with pytest.raises(ValueError):
+        parse_argv(["positional"])
+    with pytest.raises(ValueError):
+        parse_argv(["--hv", "x", "--hv.local-steps", "2"])                             # scalar / section conflict
