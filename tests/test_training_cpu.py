@@ -93,3 +93,17 @@ def test_train_diloco_torch_two_workers_gloo(tmp_path):
     assert [d["step"] for d in m] == list(range(1, 8))
     assert m[-1]["effective_step"] == 14 and "eval_loss" in m[3] and any(k.startswith("activation/") for k in m[4])
     assert all(np.isfinite(d["Loss"]) for d in m)
+
+
+def test_no_wait_strategy_through_the_cli(tmp_path):
+    """2 DiLoCo workers with --hv.all_reduce_strategy NO_WAIT: rounds are formed through the board; with both workers
+    punctual every round is a full one, so the losses equal the WAIT_FOR_ALL run step by step."""
+    la, lb = f"{tmp_path}/wait.pkl", f"{tmp_path}/nowait.pkl"
+    hv = ["--hv.local_steps", "3", "--hv.galaxy_size", "2", "--hv.skip_load_from_peers", "--total_batch_size", "8", "--max_steps", "7"]
+    torchrun(2, "opendiloco_b200.train_fsdp", BASE + hv + ["--project", la])
+    torchrun(2, "opendiloco_b200.train_fsdp", BASE + hv + ["--hv.all_reduce_strategy", "NO_WAIT", "--hv.matchmaking_time", "20",
+                                                          "--project", lb])
+    a, b = _load(la), _load(lb)
+    assert set(a) == set(b) == set(range(1, 8))
+    for s in a:
+        assert np.allclose(a[s][0], b[s][0], atol=1e-4), f"step {s}: {a[s][0]} vs {b[s][0]}"
