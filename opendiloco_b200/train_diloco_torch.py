@@ -32,7 +32,7 @@ from .parallel.compression import get_compression
 from .parallel.diloco import DiLoCoOptimizer
 from .parallel.swarm import DHT
 from .utils.config import BaseConfig, parse_argv
-from .utils.data import TEST_VOCAB_SIZE, get_fake_dataloader, get_text_dataloader
+from .utils.data import TEST_VOCAB_SIZE, TokenFileLoader, get_fake_dataloader, get_text_dataloader
 from .utils.logger import get_logger, make_metric_logger
 from .utils.metrics import get_grad_norm, register_metrics_hooks
 from .utils.training import get_cosine_schedule_with_warmup
@@ -63,6 +63,8 @@ class TorchDilocoConfig(BaseConfig):
     outer_lr: float = 0.7
     # additions for offline / test use
     fake_data: bool = False
+    token_shards: str | None = None         # glob of pre-tokenised shards (scripts/tokenize_corpus.py) instead of streaming C4
+    eval_token_shards: str | None = None
     max_steps: int | None = None
     metric_logger_type: Literal["wandb", "dummy"] = "wandb"
     seed: int = 0
@@ -160,6 +162,12 @@ def main(cfg: TorchDilocoConfig) -> None:
         vocab = min(TEST_VOCAB_SIZE, model.config.vocab_size)
         loader = get_fake_dataloader(cfg.seq_length, cfg.per_device_train_batch_size, vocab, seed=cfg.seed * 100_003 + rank)
         eval_loader = get_fake_dataloader(cfg.seq_length, cfg.per_device_train_batch_size, vocab, seed=999_983) if cfg.eval_steps else None
+    elif cfg.token_shards is not None:
+        # pre-tokenised shards (scripts/tokenize_corpus.py): mmap + native prefetch thread, no tokenizer in the loop
+        loader = TokenFileLoader(cfg.token_shards, cfg.per_device_train_batch_size, cfg.seq_length, rank=rank, world=world,
+                                 seed=cfg.seed if cfg.seed_data is None else cfg.seed_data)
+        eval_loader = TokenFileLoader(cfg.eval_token_shards or cfg.token_shards, cfg.per_device_train_batch_size, cfg.seq_length,
+                                      seed=999_983) if cfg.eval_steps else None
     else:
         loader = get_text_dataloader("allenai/c4", "mistralai/Mistral-7B-v0.1", cfg.seq_length, cfg.per_device_train_batch_size,
                                      rank, world, num_workers=0, pad_to_max=False, c4_tiny=cfg.c4_tiny, seed=cfg.seed_data)

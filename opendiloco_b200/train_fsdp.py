@@ -38,7 +38,7 @@ from .parallel.swarm import DHT, log_visible_maddrs
 from .utils.ckpt import (CKPT_PREFIX, CkptConfig, check_checkpoint_path_access, delete_old_checkpoints,
                          get_diloco_rank_dir_name, get_resume_info, load_checkpoint, save_checkpoint)
 from .utils.config import BaseConfig, parse_argv
-from .utils.data import TEST_VOCAB_SIZE, data_rank, get_fake_dataloader, get_text_dataloader
+from .utils.data import TEST_VOCAB_SIZE, TokenFileLoader, data_rank, get_fake_dataloader, get_text_dataloader
 from .utils.logger import get_logger, make_metric_logger
 from .utils.metrics import register_metrics_hooks
 from .utils.training import get_cosine_schedule_with_warmup
@@ -131,6 +131,10 @@ def get_dataloader(config: Config, topo: comm.Topology, vocab_size: int):
     if config.fake_data:
         return get_fake_dataloader(config.seq_length, config.per_device_train_batch_size, min(TEST_VOCAB_SIZE, vocab_size),
                                    num_workers=0, seed=config.seed * 100_003 + shard)
+    if config.dataset_name_or_path.startswith("tokens:"):
+        # pre-tokenised shards (scripts/tokenize_corpus.py): mmap + native prefetch thread, no tokenizer in the loop
+        return TokenFileLoader(config.dataset_name_or_path[len("tokens:"):], config.per_device_train_batch_size, config.seq_length,
+                               rank=shard, world=nshards, seed=config.seed)
     return get_text_dataloader(config.dataset_name_or_path, "mistralai/Mistral-7B-v0.1", config.seq_length,
                                config.per_device_train_batch_size, shard, nshards, config.num_workers, pad_to_max=True,
                                c4_tiny=config.c4_tiny)

@@ -15,6 +15,8 @@ from __future__ import annotations
 
 from typing import Any, Generator, Iterator
 
+import os
+
 import torch
 from torch.utils.data import IterableDataset
 
@@ -92,13 +94,12 @@ class SyntheticTokenLoader:
         self.batches_yielded = int(sd["batches_yielded"])
 
 
-class NativeTokenLoader:
-    """SyntheticTokenLoader backed by the C++ prefetcher (``csrc/host/tokengen.cc``): a background thread keeps a ring
-    of PINNED [B, S] int64 buffers filled, so ``next()`` is a pointer hand-off and the H2D copy is the only per-batch
-    host work.  The stream is a pure function of (seed, rank, batch index) => ``state_dict`` is one integer."""
+class _RingLoader:
+    """Consumer side of the C++ prefetch ring (``csrc/host/prefetch_ring.h``): a background thread keeps a ring of PINNED
+    [B, S] int64 buffers filled, ``next()`` is a pointer hand-off and the H2D copy is the only per-batch host work.  A
+    stream is a pure function of the batch index, so ``state_dict`` is one integer."""
 
-    def __init__(self, batch_size: int, seq_len: int, vocab_size: int = TEST_VOCAB_SIZE, seed: int = 0, rank: int = 0,
-                 nbuf: int = 8, pin_memory: bool | None = None):
+    def __init__(self, batch_size: int, seq_len: int, nbuf: int, pin_memory: bool | None):
         import ctypes
 
         from .. import _lib
@@ -116,19 +117,17 @@ class NativeTokenLoader:
         lib.odb_tg_position.restype = ctypes.c_int64
         lib.odb_tg_destroy.argtypes = [ctypes.c_void_p]
         pin = torch.cuda.is_available() if pin_memory is None else pin_memory
-        self.batch_size, self.seq_len, self.vocab_size = batch_size, seq_len, vocab_size
-        self.seed = (seed * 1_000_003 + rank) & 0xFFFFFFFFFFFFFFFF
+        self.batch_size, self.seq_len = batch_size, seq_len
         self.bufs = [torch.empty(batch_size, seq_len, dtype=torch.int64, pin_memory=pin) for _ in range(nbuf)]
         self._h = None
         self._held: int | None = None
         self._inflight: list = []          # (slot, cuda event) pairs whose H2D copy may still be running
-        self._start(0)
 
-    def _start(self, batch_index: int) -> None:
-        ct = self._ct
-        arr = (ct.c_void_p * len(self.bufs))(*[b.data_ptr() for b in self.bufs])
-        self._h = self._lib.odb_tg_create(self.seed, 3, self.vocab_size, self.batch_size * self.seq_len, len(self.bufs), arr,
-                                          batch_index)
+    def _buf_array(self):
+        return (self._ct.c_void_p * len(self.bufs))(*[b.data_ptr() for b in self.bufs])
+
+    def _start(self, batch_index: int) -> None:        # pragma: no cover - provided by the subclasses
+        raise NotImplementedError
 
     def __iter__(self):
         return self
@@ -173,6 +172,87 @@ class NativeTokenLoader:
             self.close()
         except Exception:
             pass
+
+
+class NativeTokenLoader(_RingLoader):
+    """SyntheticTokenLoader backed by the C++ prefetcher (``csrc/host/tokengen.cc``): uniform tokens in [3, vocab), a
+    pure function of (seed, rank, batch index)."""
+
+    def __init__(self, batch_size: int, seq_len: int, vocab_size: int = TEST_VOCAB_SIZE, seed: int = 0, rank: int = 0,
+                 nbuf: int = 8, pin_memory: bool | None = None):
+        super().__init__(batch_size, seq_len, nbuf, pin_memory)
+        self.vocab_size = vocab_size
+        self.seed = (seed * 1_000_003 + rank) & 0xFFFFFFFFFFFFFFFF
+        self._start(0)
+
+    def _start(self, batch_index: int) -> None:
+        self._h = self._lib.odb_tg_create(self.seed, 3, self.vocab_size, self.batch_size * self.seq_len, len(self.bufs),
+                                          self._buf_array(), batch_index)
+
+
+TOKEN_SHARD_MAGIC = b"ODBTOK1\0"
+
+
+def write_token_shard(path: str, tokens, bytes_per_token: int | None = None) -> None:
+    """Write a 1-D token array as one shard of the pre-tokenised corpus format (32-byte header + uint16 / uint32 tokens;
+    ``csrc/host/tokenfile.cc``).  uint16 is chosen automatically when every token fits."""
+    import ctypes
+
+    from .. import _lib
+
+    t = torch.as_tensor(tokens, dtype=torch.int64).contiguous().view(-1)
+    if bytes_per_token is None:
+        bytes_per_token = 2 if (t.numel() == 0 or int(t.max()) <= 0xFFFF) else 4
+    lib = _lib.host_lib()
+    if lib is None or not hasattr(lib, "odb_tf_write"):
+        raise RuntimeError("libodbhost.so is not built (python -m opendiloco_b200.build)")
+    lib.odb_tf_write.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]
+    rc = lib.odb_tf_write(str(path).encode(), t.data_ptr(), t.numel(), int(bytes_per_token))
+    if rc != 0:
+        raise OSError(f"could not write token shard {path} (code {rc}: token out of range for {bytes_per_token}-byte storage?)")
+
+
+class TokenFileLoader(_RingLoader):
+    """Causal-LM batches straight from pre-tokenised shards (``csrc/host/tokenfile.cc``): mmap + prefetch thread, windows
+    of ``seq_len`` tokens, seeded shuffle that visits every window once per epoch, disjoint samples per rank.  Feeds the
+    ~6 M tokens/s an 8xB200 box consumes, which on-the-fly tokenisation (the reference's pipeline) cannot.
+
+    ``paths``: shard files, or one glob pattern.  Shards come from ``write_token_shard`` / ``scripts/tokenize_corpus.py``;
+    header-less ``.bin`` files of uint16 / uint32 tokens work with ``raw_bytes_per_token``."""
+
+    def __init__(self, paths, batch_size: int, seq_len: int, rank: int = 0, world: int = 1, seed: int = 0, shuffle: bool = True,
+                 nbuf: int = 8, pin_memory: bool | None = None, raw_bytes_per_token: int = 2):
+        import glob as _glob
+
+        super().__init__(batch_size, seq_len, nbuf, pin_memory)
+        if isinstance(paths, (str, os.PathLike)):
+            found = sorted(_glob.glob(str(paths)))
+            paths = found if found else [str(paths)]
+        self.paths = [str(p) for p in paths]
+        self.rank, self.world, self.seed, self.shuffle, self.raw_bytes = rank, world, seed, shuffle, raw_bytes_per_token
+        ct = self._ct
+        self._lib.odb_tf_open.restype = ct.c_void_p
+        self._lib.odb_tf_open.argtypes = [ct.POINTER(ct.c_char_p), ct.c_int, ct.c_int, ct.c_int64, ct.c_int64, ct.c_int64, ct.c_int64,
+                                          ct.c_uint64, ct.c_int, ct.c_int, ct.POINTER(ct.c_void_p), ct.c_int64, ct.POINTER(ct.c_int64)]
+        self.windows_per_epoch = 0
+        self._start(0)
+
+    def _start(self, batch_index: int) -> None:
+        ct = self._ct
+        arr = (ct.c_char_p * len(self.paths))(*[p.encode() for p in self.paths])
+        windows = ct.c_int64(0)
+        self._h = self._lib.odb_tf_open(arr, len(self.paths), self.raw_bytes, self.seq_len, self.batch_size, self.rank, self.world,
+                                        self.seed & 0xFFFFFFFFFFFFFFFF, int(self.shuffle), len(self.bufs), self._buf_array(),
+                                        batch_index, ct.byref(windows))
+        self.windows_per_epoch = int(windows.value)
+        if not self._h:
+            raise ValueError(f"could not open token shards {self.paths[:3]}...: unreadable file, or fewer than "
+                             f"batch_size * world = {self.batch_size * self.world} windows of {self.seq_len} tokens "
+                             f"({self.windows_per_epoch} found)")
+
+    @property
+    def batches_per_epoch(self) -> int:
+        return self.windows_per_epoch // (self.batch_size * self.world)
 
 
 def data_rank(world_rank: int | None, galaxy_size: int | None, world_size: int, rank: int, local_rank: int) -> tuple[int, int]:

@@ -254,3 +254,55 @@ def test_cli_flag_grammar_matches_the_reference_launch_lines():
         parse_argv(["positional"])
     with pytest.raises(ValueError):
         parse_argv(["--hv", "x", "--hv.local-steps", "2"])                             # scalar / section conflict
+
+
+@needs_host
+def test_token_file_loader_covers_the_corpus_once_per_epoch(tmp_path):
+    """csrc/host/tokenfile.cc: shards are cut into seq_len windows; with the seeded shuffle every window is served exactly
+    once per epoch, ranks read disjoint samples, the stream is resumable from one integer, raw uint16 files work too."""
+    import numpy as np
+
+    from opendiloco_b200.utils.data import TOKEN_SHARD_MAGIC, TokenFileLoader, write_token_shard
+
+    S = 16
+    a = torch.arange(0, 40 * S + 5)                     # 40 windows (+ a dropped tail), tokens identify their position
+    b = torch.arange(100_000, 100_000 + 24 * S)         # 24 windows, needs 4-byte storage
+    write_token_shard(tmp_path / "a.tok", a)
+    write_token_shard(tmp_path / "b.tok", b)
+    assert (tmp_path / "a.tok").read_bytes()[:8] == TOKEN_SHARD_MAGIC
+    assert (tmp_path / "a.tok").stat().st_size == 32 + 2 * a.numel() and (tmp_path / "b.tok").stat().st_size == 32 + 4 * b.numel()
+    with pytest.raises(OSError):
+        write_token_shard(tmp_path / "bad.tok", torch.tensor([70000]), bytes_per_token=2)
+
+    world, B = 2, 4
+    loaders = [TokenFileLoader(str(tmp_path / "*.tok"), B, S, rank=r, world=world, seed=7, pin_memory=False) for r in range(world)]
+    assert loaders[0].windows_per_epoch == 64 and loaders[0].batches_per_epoch == 8
+    starts = []
+    for _ in range(8):                                  # one epoch
+        for ld in loaders:
+            batch = next(ld)["input_ids"]
+            assert batch.shape == (B, S)
+            for row in batch:
+                assert torch.equal(row, row[0] + torch.arange(S))        # a window is contiguous text
+                starts.append(int(row[0]))
+    expected = [int(x) for x in a[: 40 * S : S]] + [int(x) for x in b[::S]]
+    assert sorted(starts) == sorted(expected)           # every window exactly once, none twice
+    assert starts != sorted(starts)                     # and not in file order
+    nxt = [next(ld)["input_ids"].clone() for ld in loaders]              # epoch 2 starts: a different permutation
+    assert not torch.equal(nxt[0][:, 0], torch.tensor(starts[:B]))
+    # resume: same seed + position => same batches
+    st = loaders[0].state_dict()
+    want = [next(loaders[0])["input_ids"].clone() for _ in range(3)]
+    fresh = TokenFileLoader(str(tmp_path / "*.tok"), B, S, rank=0, world=world, seed=7, pin_memory=False)
+    fresh.load_state_dict(st)
+    assert all(torch.equal(next(fresh)["input_ids"], w) for w in want)
+    # sequential order without shuffle; raw header-less uint16 file
+    seq = TokenFileLoader([str(tmp_path / "a.tok")], 2, S, shuffle=False, pin_memory=False)
+    assert torch.equal(next(seq)["input_ids"][:, 0], torch.tensor([0, S]))
+    np.arange(0, 10 * S, dtype=np.uint16).tofile(tmp_path / "raw.bin")
+    raw = TokenFileLoader([str(tmp_path / "raw.bin")], 2, S, shuffle=False, pin_memory=False, raw_bytes_per_token=2)
+    assert torch.equal(next(raw)["input_ids"][1], S + torch.arange(S))
+    with pytest.raises(ValueError):
+        TokenFileLoader([str(tmp_path / "raw.bin")], 64, S, pin_memory=False)          # fewer windows than one batch
+    for ld in loaders + [fresh, seq, raw]:
+        ld.close()

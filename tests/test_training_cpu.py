@@ -107,3 +107,23 @@ def test_no_wait_strategy_through_the_cli(tmp_path):
     assert set(a) == set(b) == set(range(1, 8))
     for s in a:
         assert np.allclose(a[s][0], b[s][0], atol=1e-4), f"step {s}: {a[s][0]} vs {b[s][0]}"
+
+
+def test_training_on_pretokenised_shards(tmp_path):
+    """scripts/tokenize_corpus.py (byte-level fallback tokenizer) -> shards -> train_fsdp with --dataset_name_or_path tokens:...:
+    the native mmap / prefetch loader feeds the driver, 2 data-parallel ranks read disjoint windows, and the loss falls on
+    (highly repetitive) real text."""
+    src = tmp_path / "corpus.txt"
+    src.write_text("".join(f"the quick brown fox number {i % 7} jumps over the lazy dog again and again.\n" for i in range(600)))
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "tokenize_corpus.py"), "--input", str(src), "--output-dir",
+                          str(tmp_path / "tok"), "--tokenizer", "byte", "--shard-tokens", "20000"],
+                         env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert len(os.listdir(tmp_path / "tok")) >= 2
+    log = f"{tmp_path}/tok.pkl"
+    args = [a for a in BASE if a != "--fake_data"] + ["--dataset_name_or_path", f"tokens:{tmp_path}/tok/*.tok", "--max_steps", "10",
+                                                      "--total_batch_size", "8", "--project", log]
+    torchrun(2, "opendiloco_b200.train_fsdp", args)
+    losses = _load(log)
+    assert set(losses) == set(range(1, 11))
+    assert losses[10][0] < losses[1][0] - 1.0
