@@ -130,13 +130,16 @@ def build_host(force: bool = False) -> Path:
 
 
 def build_all(force: bool = False, verbose: bool = False) -> dict[str, Path]:
-    return {"cuda": build_cuda(force, verbose), "host": build_host(force)}
+    host = build_host(force)          # first: it needs only g++, so it survives on machines without nvcc (CPU CI)
+    return {"cuda": build_cuda(force, verbose), "host": host}
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true", help="print ptxas -v output (registers / spills / smem)")
+    ap.add_argument("--host-only", action="store_true", help="build libodbhost.so only (no CUDA toolkit needed)")
     a = ap.parse_args()
-    for k, v in build_all(a.force, a.verbose).items():
+    built = {"host": build_host(a.force)} if a.host_only else build_all(a.force, a.verbose)
+    for k, v in built.items():
         print(f"{k}: {v} ({v.stat().st_size if v.exists() else 0} bytes)")
