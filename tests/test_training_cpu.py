@@ -127,3 +127,20 @@ def test_training_on_pretokenised_shards(tmp_path):
     losses = _load(log)
     assert set(losses) == set(range(1, 11))
     assert losses[10][0] < losses[1][0] - 1.0
+
+
+@pytest.mark.parametrize("saved,resumed", [("SHARD_GRAD_OP", "NO_SHARD"), ("NO_SHARD", "SHARD_GRAD_OP")])
+def test_checkpoint_is_resharded_on_load(tmp_path, saved, resumed):
+    """Checkpoints hold flat [lo, hi) slices of the parameter / optimizer arenas, so a run saved under one sharding strategy
+    resumes under another (the reference's DCP checkpoints are tied to the FSDP wrapping they were written with)."""
+    ckpt = f"{tmp_path}/ckpt"
+    log1, log2 = f"{tmp_path}/log1.pkl", f"{tmp_path}/log2.pkl"
+    torchrun(2, "opendiloco_b200.train_fsdp", BASE + ["--max_steps", "8", "--sharding_strategy", saved, "--ckpt.path", ckpt,
+                                                      "--ckpt.interval", "4", "--project", log1])
+    torchrun(2, "opendiloco_b200.train_fsdp", BASE + ["--max_steps", "8", "--sharding_strategy", resumed, "--ckpt.path", ckpt,
+                                                      "--ckpt.resume", f"{ckpt}/model_step_4", "--project", log2])
+    a, b = _load(log1), _load(log2)
+    assert set(a) & set(b) == {5, 6, 7, 8}
+    for s in (5, 6, 7, 8):
+        assert np.allclose(a[s][0], b[s][0], atol=1e-3), f"Loss at step {s} is different: {a[s][0]} vs {b[s][0]}"
+        assert a[s][1] == b[s][1]
