@@ -144,3 +144,15 @@ def test_checkpoint_is_resharded_on_load(tmp_path, saved, resumed):
     for s in (5, 6, 7, 8):
         assert np.allclose(a[s][0], b[s][0], atol=1e-3), f"Loss at step {s} is different: {a[s][0]} vs {b[s][0]}"
         assert a[s][1] == b[s][1]
+
+
+@pytest.mark.parametrize("precision", ["fp16-mixed", "32-true"])
+def test_other_precision_modes_run(tmp_path, precision):
+    """fp16-mixed drives the GradScaler path (train_fsdp.py:383-405: unscale -> clip -> scaler.step -> update), 32-true the
+    pure fp32 engine; bf16-mixed is what every other test uses."""
+    log = f"{tmp_path}/p.pkl"
+    args = [a for a in BASE]
+    args[args.index("--precision") + 1] = precision
+    torchrun(1, "opendiloco_b200.train_fsdp", args + ["--max_steps", "4", "--total_batch_size", "8", "--project", log])
+    losses = _load(log)
+    assert set(losses) == {1, 2, 3, 4} and all(np.isfinite(v[0]) for v in losses.values())
