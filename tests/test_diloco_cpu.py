@@ -208,3 +208,39 @@ def test_elastic_no_wait_rounds_gloo():
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
     assert "FAIL" not in res.stdout and res.stdout.count("ALL OK") == 3
+
+
+def test_reference_import_paths_resolve():
+    """Code written against PrimeIntellect-ai/OpenDiloco imports from ``open_diloco.*``; the shim package maps those paths
+     onto this framework - including a solo optimizer built exactly like the reference README does."""
+    from functools import partial
+
+    import open_diloco.ckpt_utils as ck
+    import open_diloco.hivemind_diloco as hd
+    import open_diloco.utils as ut
+    from open_diloco.hivemind_diloco import AllReduceStrategy as ARS
+    from open_diloco.hivemind_diloco import DiLoCoGradAverager as GA
+    from open_diloco.hivemind_diloco import DiLoCoOptimizer as Opt
+
+    assert Opt is DiLoCoOptimizer and ARS is AllReduceStrategy and GA is DiLoCoGradAverager
+    for name in ("DiLoCoStateAverager", "DiloCoProgressTracker"):
+        assert hasattr(hd, name)
+    for name in ("FakeTokenizedDataset", "get_compression_kwargs", "get_sharding_strategy", "found_inf_grad", "hash_tensor_content",
+                 "register_metrics_hooks", "DummyLogger", "WandbLogger", "Logger", "log_activations_hook", "get_grad_norm"):
+        assert hasattr(ut, name), name
+    for name in ("CkptConfig", "get_resume_info", "save_checkpoint", "load_checkpoint", "delete_old_checkpoints",
+                 "check_checkpoint_path_access", "get_diloco_rank_dir_name", "filter_ckpt_files"):
+        assert hasattr(ck, name), name
+    import open_diloco.train_diloco_torch  # noqa: F401
+    import open_diloco.train_fsdp as tf
+
+    assert hasattr(tf, "Config") and hasattr(tf, "HvConfig") and hasattr(tf, "train")
+    lin = torch.nn.Linear(4, 2)
+    opt = Opt(dht=None, run_id="llama", batch_size=8, num_inner_steps=2, params=list(lin.parameters()),
+              outer_optimizer=partial(torch.optim.SGD, lr=0.7, momentum=0.9, nesterov=True),
+              inner_optimizer=partial(torch.optim.AdamW, lr=1e-3, weight_decay=0.1, betas=(0.9, 0.95)))
+    for _ in range(2):
+        lin(torch.randn(3, 4)).sum().backward()
+        opt.step()
+        opt.zero_grad()
+    assert opt.local_epoch == 1 and set(opt.state_dict()) >= {"state_dict_outer", "state_dict_inner"}
