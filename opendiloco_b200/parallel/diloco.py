@@ -189,6 +189,9 @@ class DiloCoProgressTracker:
             if int(e) >= epoch:
                 eta = max(eta, max(0, self.target_batch_size - int(s)) / max(float(sps), 1e-9))
         self._global_epoch_hint = max(self._global_epoch_hint, epoch)
+        # the swarm status line hivemind prints per fetch (hivemind_diloco.py:269-272)
+        logger.debug(f"{self.prefix} has taken {self.local_step} local steps. Peers: {alive}, epoch: {epoch}, "
+                     f"steps: {self.real_step}. ETA: {eta:.2f}")
         self.global_progress = GlobalTrainingProgress(epoch, 0, self.target_batch_size, num_peers=max(alive, 1),
                                                       num_clients=0, eta_next_epoch=now + eta,
                                                       next_fetch_time=now + min(max(eta, self.min_refresh_period),
