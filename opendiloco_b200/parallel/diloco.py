@@ -564,7 +564,8 @@ class DiLoCoOptimizer:
         topts.setdefault("max_refresh_period", 2)
         self.tracker = DiloCoProgressTracker(batch_size, num_inner_steps, dht=dht, prefix=run_id,
                                              target_batch_size=batch_size * num_inner_steps,
-                                             publish=all_reduce_strategy == AllReduceStrategy.NO_WAIT, **topts)
+                                             publish=(all_reduce_strategy == AllReduceStrategy.NO_WAIT
+                                                      or getattr(dht, "board", None) is not None), **topts)
         self._schema_hash = self._compute_schema_hash()
         self._fused = None
         want_fused = fused_collective if fused_collective is not None else True

@@ -225,3 +225,19 @@ def parse_address(addr: str) -> tuple[str, int] | None:
             if host and port.isdigit():
                 return host, int(port)
     return None
+
+
+if __name__ == "__main__":          # python -m opendiloco_b200.parallel.rendezvous --serve 29400
+    import argparse
+    import signal
+
+    ap = argparse.ArgumentParser(description="host the swarm membership board")
+    ap.add_argument("--serve", type=int, default=29400, metavar="PORT")
+    a = ap.parse_args()
+    srv = RendezvousServer(a.serve)
+    print(f"swarm board listening on odb://0.0.0.0:{srv.port}  (export ODB_BOARD=odb://<host>:{srv.port})", flush=True)
+    stop = threading.Event()
+    signal.signal(signal.SIGTERM, lambda *_: stop.set())
+    signal.signal(signal.SIGINT, lambda *_: stop.set())
+    stop.wait()
+    srv.stop()

@@ -25,6 +25,12 @@ echo "Initial peer: $INITIAL_PEER"
 mkdir -p logs
 HERE="$(cd "$(dirname "$0")" && pwd)"
 
+# optional native membership board (heartbeats / progress records visible to scripts/swarm_status.py): DILOCO_BOARD_PORT=29500
+if [ -n "${DILOCO_BOARD_PORT:-}" ]; then
+    PYTHONPATH="$HERE" python -m opendiloco_b200.parallel.rendezvous --serve "$DILOCO_BOARD_PORT" > logs/board.log 2>&1 &
+    export ODB_BOARD="odb://127.0.0.1:${DILOCO_BOARD_PORT}"
+fi
+
 for i in $(seq 0 $(( N - 1 ))); do
     extra_env=""
     if [ "$i" -gt 0 ]; then export_wandb="WANDB_MODE=disabled"; else export_wandb=""; fi
