@@ -36,7 +36,7 @@ def snapshot(board: rdv.RendezvousClient, prefix: str, n: int) -> list[str]:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("address", help="odb://host:port of the board (ODB_BOARD of the job)")
-    ap.add_argument("--prefix", default="diloco", help="tracker prefix (<run_id>_tracker style prefixes are passed verbatim)")
+    ap.add_argument("--prefix", default="llama", help="tracker prefix = the run_id of the job (train_fsdp uses \"llama\")")
     ap.add_argument("--galaxy-size", type=int, default=8)
     ap.add_argument("--watch", type=float, default=0.0, help="refresh period in seconds (0 = print once)")
     a = ap.parse_args()

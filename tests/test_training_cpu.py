@@ -19,8 +19,8 @@ def free_port() -> int:
         return s.getsockname()[1]
 
 
-def torchrun(nproc: int, module: str, args: list[str], timeout: int = 900) -> None:
-    env = dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2", WANDB_MODE="disabled")
+def torchrun(nproc: int, module: str, args: list[str], timeout: int = 900, extra_env: dict | None = None) -> None:
+    env = dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2", WANDB_MODE="disabled", **(extra_env or {}))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
            "--master-port", str(free_port()), "-m", module, *args]
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout)
@@ -156,3 +156,27 @@ def test_other_precision_modes_run(tmp_path, precision):
     torchrun(1, "opendiloco_b200.train_fsdp", args + ["--max_steps", "4", "--total_batch_size", "8", "--project", log])
     losses = _load(log)
     assert set(losses) == {1, 2, 3, 4} and all(np.isfinite(v[0]) for v in losses.values())
+
+
+def test_swarm_runs_on_the_native_board(tmp_path):
+    """2 DiLoCo workers with ODB_BOARD pointing at the native membership board hosted by this test process: progress records
+    and the outer-step handshake go through it (not the c10d store), the run finishes and the board holds the traces."""
+    from opendiloco_b200.parallel import rendezvous as rdv
+
+    if not rdv.available():
+        pytest.skip("libodbhost.so not built")
+    server = rdv.RendezvousServer(0)
+    try:
+        log = f"{tmp_path}/board.pkl"
+        hv = ["--hv.local_steps", "2", "--hv.galaxy_size", "2", "--hv.skip_load_from_peers", "--hv.timeout_waiting_for_peers", "60",
+              "--total_batch_size", "8", "--max_steps", "5"]
+        torchrun(2, "opendiloco_b200.train_fsdp", BASE + hv + ["--project", log], extra_env={"ODB_BOARD": f"odb://127.0.0.1:{server.port}"})
+        assert set(_load(log)) == set(range(1, 6))
+        board = rdv.RendezvousClient("127.0.0.1", server.port)
+        for r in (0, 1):
+            rec = board.get(f"llama_progress/worker-{r}")          # tracker prefix = run_id ("llama", train_fsdp.py:300)
+            assert rec is not None and rec.decode().count(",") == 3
+        assert server.num_keys() >= 4            # progress records + the arrival keys of two outer steps
+        board.close()
+    finally:
+        server.stop()
