@@ -13,7 +13,6 @@ LM head + shifted CE :484-491 / loss_utils.py:45-67.
 """
 from __future__ import annotations
 
-import json
 import os
 from dataclasses import dataclass
 from pathlib import Path

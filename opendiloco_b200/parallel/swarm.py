@@ -14,9 +14,8 @@ import contextlib
 import os
 import threading
 import time
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
-import torch
 import torch.distributed as dist
 
 from . import comm

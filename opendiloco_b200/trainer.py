@@ -12,9 +12,7 @@ device->host read unless the caller asks for the loss value.
 """
 from __future__ import annotations
 
-import math
-import time
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from functools import partial
 from typing import Iterator
 
