@@ -23,6 +23,17 @@
 //              C = gu [M, 2I], turns them IN PLACE into d(gate) / d(up) and stores them back - d(act) never reaches memory
 //   kRoPE    : C is the packed qkv buffer; 64-column chunks are heads; chunks below `rope_cols` are rotated with the
 //              HF rotate-half convention using fp32 cos/sin tables (position = row % S)
+//   kLCEFwd  : fused linear-cross-entropy forward.  The accumulator holds a tile of LM-head logits z;
+//              the epilogue turns it into shifted exponentials e = exp(z - c_row) (c_row = the row's label logit, so
+//              sum_v e >= 1 and loss_row = log sum_v e), accumulates the row sums into per-tile partial planes and
+//              (training only) stores bf16(e).  Neither logits nor a log-softmax pass ever exist; in evaluation mode
+//              (store = 0) nothing of size [T, V] is written at all.
+//   kLCEdX   : dgrad of the LM head on the shifted exponentials: out = rowscale * acc - g * W[label]  (softmax - onehot
+//              is never formed: the per-row normaliser is applied to the fp32 accumulator, the one-hot term is a gather)
+//
+// B_MN = true: the B operand is stored [K, N] row-major (N contiguous, "MN-major"): C = A * B.  This is the dgrad form
+// dX = dY * W with W in its forward [out, in] layout, so no transposed weight copy is needed (the 64 x 64 boxes and the
+// LBO / SBO descriptor fields are the ones the weight-gradient kernel uses for both of its operands).
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -42,7 +53,8 @@ constexpr int EPI_GROUPS = 2;
 constexpr int GROUP_M = 16;           // rasterisation: 16 m-blocks x all n-blocks per super-block (L2 reuse of A and B)
 constexpr uint32_t TMEM_COLS = 512;
 
-enum Epi { kStore = 0, kSwiGLU = 1, kRoPE = 2, kSwiGLUBwd = 3 };
+enum Epi { kStore = 0, kSwiGLU = 1, kRoPE = 2, kSwiGLUBwd = 3, kLCEFwd = 4, kLCEdX = 5 };
+constexpr int BOX_BYTES = 64 * 64 * 2;    // MN-major B: one 64(k) x 64(n) box
 
 template <int EPI> struct Cfg { static constexpr int STAGES = 5, NBUF = 4; };     // NBUF: staging tiles (2 per epilogue group)
 template <> struct Cfg<kSwiGLU> { static constexpr int STAGES = 4, NBUF = 6; };   // 3 per epilogue group
@@ -70,6 +82,16 @@ struct Params {
   const float* sin_t;
   int ks1, ks2;              // A operand split along K into up to three tensors: k-blocks [0,ks1) from A, [ks1,ks2) from A1,
                              // [ks2,..) from A2 (0/0 = single tensor).  Lets dq|dk|dv feed one dgrad GEMM without packing.
+  // ---- fused linear-cross-entropy
+  const float* row_shift;    // kLCEFwd: c_row [M] (label logit; 0 for ignored rows)
+  float* partials;           // kLCEFwd: [2 * num_n (+ 2 * num_n when want_sumsq)][M] partial row sums of exp(z - c)
+  int want_sumsq;            // kLCEFwd: also accumulate sum z^2 (lm_head activation norm) into the second half of partials
+  int store;                 // kLCEFwd: 1 = write bf16(e) to C (training) ; 0 = statistics only (evaluation)
+  const float* rowscale;     // kLCEdX: s_row [M] = gscale / sum_v e  (0 for ignored rows)
+  const long long* labels;   // kLCEdX: [M], < 0 = ignored
+  const float* gscale;       // kLCEdX: device scalar loss_scale / n_valid
+  const __nv_bfloat16* wlab; // kLCEdX: the LM-head weight [V, N] (row stride ldwlab) for the one-hot gather
+  long long ldwlab;
 };
 
 // write one 64-column chunk of this thread's row into the swizzled staging tile (row r, 8 x 16-byte chunks)
@@ -84,7 +106,7 @@ __device__ __forceinline__ void stage_row_bf16(uint8_t* buf, int row, const floa
   }
 }
 
-template <int EPI>
+template <int EPI, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_aux,
@@ -143,14 +165,19 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           int b_row;
           if constexpr (EPI == kSwiGLU) b_row = (cta_rank == 0) ? n_blk * (BN / 2) : p.I + n_blk * (BN / 2);   // gate half | up half
           else b_row = n_blk * BN + (int)cta_rank * (BN / 2);
-          tma_load_2d_2cta(smem_b + stage * B_BYTES, &tmap_b, leader_full, kb * BK, b_row);
+          if constexpr (B_MN) {      // B is [K, N] row-major: two 64(k) x 64(n) boxes cover this CTA's 128 n-values
+            tma_load_2d_2cta(smem_b + stage * B_BYTES, &tmap_b, leader_full, b_row, kb * BK);
+            tma_load_2d_2cta(smem_b + stage * B_BYTES + BOX_BYTES, &tmap_b, leader_full, b_row + 64, kb * BK);
+          } else {
+            tma_load_2d_2cta(smem_b + stage * B_BYTES, &tmap_b, leader_full, kb * BK, b_row);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1 && cta_rank == 0) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, 0, 0);
+    constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, 0, B_MN ? 1 : 0);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -165,11 +192,14 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         tc_fence_after_sync();
         if (elect_one()) {
           const uint64_t adesc = make_smem_desc_sw128(smem_u32(smem_a + stage * A_BYTES), 16, 1024);
-          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem_b + stage * B_BYTES), 16, 1024);
+          // MN-major B: 64-element n-chunks are BOX_BYTES apart (LBO), 8-row k-groups 1024 B apart (SBO)
+          const uint64_t bdesc = B_MN ? make_smem_desc_sw128(smem_u32(smem_b + stage * B_BYTES), BOX_BYTES, 1024)
+                                      : make_smem_desc_sw128(smem_u32(smem_b + stage * B_BYTES), 16, 1024);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in descriptor units
-            umma_ss_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            // K-major: advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in descriptor units
+            // MN-major: 16 k further = 16 rows of 128 B = 2048 B = +128 units
+            umma_ss_2cta(d_tmem, adesc + 2 * k, bdesc + (B_MN ? 128 : 2) * k, idesc, (kb | k) != 0);
           }
           umma_commit_2cta(&empty_bar[stage]);                       // frees this stage in BOTH CTAs
           if (kb == num_k - 1) umma_commit_2cta(&tmem_full[acc]);    // accumulator ready in BOTH CTAs
@@ -311,6 +341,123 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             tma_store_commit();
           }
         }
+      } else if constexpr (EPI == kLCEFwd) {
+        // logits tile -> shifted exponentials + partial row sums.  Thread = one token row, this group's 2 x 64 columns.
+        constexpr float L2E = 1.4426950408889634f;
+        const int grow = m_idx + row;
+        const bool row_ok = grow < p.M;
+        const float shift = row_ok ? p.row_shift[grow] * L2E : 0.f;
+        float psum = 0.f, psq = 0.f;
+#pragma unroll 1
+        for (int c = eg; c < BN / EPI_CHUNK; c += EPI_GROUPS) {
+          float v[64];
+          {
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32b_x32(t_row + c * 64, r0);
+            tmem_ld_32x32b_x32(t_row + c * 64 + 32, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
+          }
+          if (c >= BN / EPI_CHUNK - EPI_GROUPS) {
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(leader_tmem_empty);
+          }
+          const int col0 = n_blk * BN + c * 64;
+          const int ncols = p.N - col0;                     // < 64 only in a ragged last tile; <= 0: chunk is outside
+          if (p.want_sumsq) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) psq += (j < ncols) ? v[j] * v[j] : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            // clamp: a row whose label is > 69 nats below its best logit would overflow the fp32 row sum otherwise
+            float e;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(fmaf(v[j], L2E, -shift), 100.f)));
+            v[j] = e;
+          }
+          if (ncols < 64) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] = (j < ncols) ? v[j] : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 64; ++j) psum += v[j];
+          if (p.store && ncols > 0) {
+            uint8_t* buf = my_epi + (buf_i & 1) * EPI_BYTES;
+            if (store_thread) tma_store_wait_read<1>();
+            named_bar_sync(bar_a, EPI_THREADS);
+            stage_row_bf16(buf, row, v);
+            fence_proxy_async_smem();
+            named_bar_sync(bar_b, EPI_THREADS);
+            if (store_thread) {
+              tma_store_2d(&tmap_c, buf, col0, m_idx);
+              tma_store_commit();
+            }
+            ++buf_i;
+          }
+        }
+        if (row_ok) {
+          const size_t plane = (size_t)(n_blk * EPI_GROUPS + eg);
+          p.partials[plane * p.M + grow] = psum;
+          if (p.want_sumsq) p.partials[((size_t)p.num_n * EPI_GROUPS + plane) * p.M + grow] = psq;
+        }
+      } else if constexpr (EPI == kLCEdX) {
+        const int grow = m_idx + row;
+        float rs = 0.f, g = 0.f;
+        const __nv_bfloat16* wl = nullptr;
+        if (grow < p.M) {
+          rs = p.rowscale[grow];
+          const long long y = p.labels[grow];
+          if (y >= 0) { g = *p.gscale; wl = p.wlab + (size_t)y * p.ldwlab; }
+        }
+#pragma unroll 1
+        for (int c = eg; c < BN / EPI_CHUNK; c += EPI_GROUPS) {
+          const int col0 = n_blk * BN + c * 64;
+          uint4 wv[8];
+          const bool have_w = (wl != nullptr) && (col0 + 64 <= p.N);
+          if (have_w) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) wv[j] = ld_nc_v4(wl + col0 + j * 8);      // in flight while the accumulator is read
+          }
+          float v[64];
+          {
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32b_x32(t_row + c * 64, r0);
+            tmem_ld_32x32b_x32(t_row + c * 64 + 32, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
+          }
+          if (c >= BN / EPI_CHUNK - EPI_GROUPS) {
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(leader_tmem_empty);
+          }
+          if (have_w) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float w8[8];
+              unpack8(wv[j], w8);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[j * 8 + e] = fmaf(rs, v[j * 8 + e], -g * w8[e]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] *= rs;
+          }
+          uint8_t* buf = my_epi + (buf_i & 1) * EPI_BYTES;
+          if (store_thread) tma_store_wait_read<1>();
+          named_bar_sync(bar_a, EPI_THREADS);
+          stage_row_bf16(buf, row, v);
+          fence_proxy_async_smem();
+          named_bar_sync(bar_b, EPI_THREADS);
+          if (store_thread) {
+            tma_store_2d(&tmap_c, buf, col0, m_idx);
+            tma_store_commit();
+          }
+          ++buf_i;
+        }
       } else {
         float cs[32], sn[32];
         bool rope_tile = false;
@@ -382,10 +529,16 @@ struct ASplit {
   int K0 = 0, K1 = 0, K2 = 0;      // K extents of the three A tensors (multiples of 64); K0 == 0 => no split
 };
 
-template <int EPI>
+struct LceArgs {
+  const float* row_shift = nullptr; float* partials = nullptr; int want_sumsq = 0; int store = 1;
+  const float* rowscale = nullptr; const long long* labels = nullptr; const float* gscale = nullptr;
+  const void* wlab = nullptr; long long ldwlab = 0;
+};
+
+template <int EPI, bool B_MN = false>
 static int launch(const void* A, const void* B, void* C, void* aux, int M, int N, int K, long long lda, long long ldb,
                   long long ldc, long long ldaux, int I, int S, int rope_cols, const float* cos_t, const float* sin_t,
-                  cudaStream_t st, const ASplit& sp = ASplit()) {
+                  cudaStream_t st, const ASplit& sp = ASplit(), const LceArgs& lce = LceArgs()) {
   CUtensorMap ta, tb, tc, tx, ta1, ta2;
   int rc;
   const int n_out = (EPI == kSwiGLU || EPI == kSwiGLUBwd) ? 2 * I : N;
@@ -395,8 +548,13 @@ static int launch(const void* A, const void* B, void* C, void* aux, int M, int N
     if ((rc = make_tmap_2d(&ta1, sp.A1, M, sp.K1, sp.lda1 * 2, BM, BK, 2))) return rc;
     if ((rc = make_tmap_2d(&ta2, sp.A2, M, sp.K2, sp.lda2 * 2, BM, BK, 2))) return rc;
   }
-  if ((rc = make_tmap_2d(&tb, B, (EPI == kSwiGLU) ? 2 * I : N, K, ldb * 2, BN / 2, BK, 2))) return rc;
-  if ((rc = make_tmap_2d(&tc, C, M, n_out, ldc * 2, BM, EPI_CHUNK, 2))) return rc;
+  if (B_MN) {
+    if ((rc = make_tmap_2d(&tb, B, K, N, ldb * 2, 64, 64, 2))) return rc;            // [K rows, N cols], 64 x 64 boxes
+  } else {
+    if ((rc = make_tmap_2d(&tb, B, (EPI == kSwiGLU) ? 2 * I : N, K, ldb * 2, BN / 2, BK, 2))) return rc;
+  }
+  if (EPI == kLCEFwd && !lce.store) tc = ta;       // statistics only: nothing is stored, any valid map will do
+  else if ((rc = make_tmap_2d(&tc, C, M, n_out, ldc * 2, BM, EPI_CHUNK, 2))) return rc;
   if (EPI == kSwiGLU) {
     if ((rc = make_tmap_2d(&tx, aux, M, I, ldaux * 2, BM, EPI_CHUNK, 2))) return rc;
   } else {
@@ -409,17 +567,20 @@ static int launch(const void* A, const void* B, void* C, void* aux, int M, int N
   p.I = I; p.S = S > 0 ? S : 1; p.rope_cols = rope_cols; p.cos_t = cos_t; p.sin_t = sin_t;
   p.ks1 = sp.K0 ? sp.K0 / BK : 0;
   p.ks2 = sp.K0 ? (sp.K0 + sp.K1) / BK : 0;
+  p.row_shift = lce.row_shift; p.partials = lce.partials; p.want_sumsq = lce.want_sumsq; p.store = lce.store;
+  p.rowscale = lce.rowscale; p.labels = lce.labels; p.gscale = lce.gscale;
+  p.wlab = (const __nv_bfloat16*)lce.wlab; p.ldwlab = lce.ldwlab;
   static bool attr_set = false;
   constexpr int smem = smem_bytes<EPI>();
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_tn_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_tn_kernel<EPI, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const int tiles = p.num_m * p.num_n;
   const int max_clusters = sm_count() / 2;
   const int grid = 2 * (tiles < max_clusters ? tiles : max_clusters);
-  gemm2_bf16_tn_kernel<EPI><<<grid, THREADS, smem, st>>>(ta, tb, tc, tx, ta1, ta2, p);    // cluster dims are compiled in (__cluster_dims__)
+  gemm2_bf16_tn_kernel<EPI, B_MN><<<grid, THREADS, smem, st>>>(ta, tb, tc, tx, ta1, ta2, p);    // cluster dims are compiled in (__cluster_dims__)
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }
@@ -463,4 +624,53 @@ ODB_EXPORT int odb_gemm2_bf16_tn_a3(const void* A0, const void* A1, const void* 
   gemm2::ASplit sp;
   sp.A1 = A1; sp.A2 = A2; sp.lda1 = lda1; sp.lda2 = lda2; sp.K0 = K0; sp.K1 = K1; sp.K2 = K2;
   return gemm2::launch<gemm2::kStore>(A0, B, C, nullptr, M, N, K0 + K1 + K2, lda0, ldb, ldc, 0, 0, 0, 0, nullptr, nullptr, st, sp);
+}
+
+// ---------------------------------------------------------------------------------------------------- MN-major B (dgrad)
+// C[M,N] (bf16) = A[M,K] (row stride lda) * B[K,N] (row stride ldb, N contiguous).  dX = dY * W with W as stored.
+ODB_EXPORT int odb_gemm2_bf16_nn(const void* A, const void* B, void* C, int M, int N, int K, long long lda, long long ldb,
+                                long long ldc, cudaStream_t st) {
+  if (K % 8 || N % 8 || lda % 8 || ldb % 8 || ldc % 8) return -1;
+  return gemm2::launch<gemm2::kStore, true>(A, B, C, nullptr, M, N, K, lda, ldb, ldc, 0, 0, 0, 0, nullptr, nullptr, st);
+}
+
+// as odb_gemm2_bf16_tn_a3 with B = W[K0+K1+K2, N] in its forward layout (dgrad of the fused QKV projection)
+ODB_EXPORT int odb_gemm2_bf16_nn_a3(const void* A0, const void* A1, const void* A2, long long lda0, long long lda1, long long lda2,
+                                    int K0, int K1, int K2, const void* B, void* C, int M, int N, long long ldb, long long ldc,
+                                    cudaStream_t st) {
+  if (K0 % 64 || K1 % 64 || K2 % 64 || K0 <= 0 || K1 <= 0 || K2 <= 0 || N % 8 || ldb % 8) return -1;
+  gemm2::ASplit sp;
+  sp.A1 = A1; sp.A2 = A2; sp.lda1 = lda1; sp.lda2 = lda2; sp.K0 = K0; sp.K1 = K1; sp.K2 = K2;
+  return gemm2::launch<gemm2::kStore, true>(A0, B, C, nullptr, M, N, K0 + K1 + K2, lda0, ldb, ldc, 0, 0, 0, 0, nullptr, nullptr, st, sp);
+}
+
+// SwiGLU backward fused into the down-proj dgrad, reading W_down [K = hidden, I] in its forward layout
+ODB_EXPORT int odb_gemm2_swiglu_bwd_nn(const void* dY, const void* Wd, void* gu, int M, int I, int K, long long lda, long long ldb,
+                                       cudaStream_t st) {
+  if (K % 8 || I % 64 || lda % 8 || ldb % 8) return -1;
+  return gemm2::launch<gemm2::kSwiGLUBwd, true>(dY, Wd, gu, nullptr, M, I, K, lda, ldb, 2 * I, 0, I, 0, 0, nullptr, nullptr, st);
+}
+
+// ---------------------------------------------------------------------------------------------------- fused linear-cross-entropy
+// E[M,V] (bf16, optional) = exp(X[M,K] W[V,K]^T - shift[M]) ; partials[(2*ceil(V/256)) (x2 with sumsq)][M] = partial row sums
+ODB_EXPORT int odb_lce_fwd(const void* X, const void* W, void* E, int M, int V, int K, long long ldx, long long ldw, long long lde,
+                           const void* row_shift, void* partials, int want_sumsq, int store, cudaStream_t st) {
+  if (K % 8 || ldx % 8 || ldw % 8 || (store && (lde % 8 || !E))) return -1;
+  gemm2::LceArgs a;
+  a.row_shift = (const float*)row_shift; a.partials = (float*)partials; a.want_sumsq = want_sumsq; a.store = store;
+  return gemm2::launch<gemm2::kLCEFwd, false>(X, W, E, nullptr, M, V, K, ldx, ldw, lde, 0, 0, 0, 0, nullptr, nullptr, st,
+                                               gemm2::ASplit(), a);
+}
+// number of partial planes odb_lce_fwd writes per statistic
+ODB_EXPORT int odb_lce_planes(int V) { return 2 * ((V + gemm2::BN - 1) / gemm2::BN); }
+
+// dX[M,N] (bf16) = rowscale[M] * (E[M,V] * W[V,N]) - gscale * [label >= 0] * W[label]     (N % 64 == 0)
+ODB_EXPORT int odb_lce_dx(const void* E, const void* W, void* dX, int M, int N, int V, long long lde, long long ldw, long long ldd,
+                          const void* rowscale, const void* labels, const void* gscale, cudaStream_t st) {
+  if (V % 8 || N % 64 || lde % 8 || ldw % 8 || ldd % 8) return -1;
+  gemm2::LceArgs a;
+  a.rowscale = (const float*)rowscale; a.labels = (const long long*)labels; a.gscale = (const float*)gscale;
+  a.wlab = W; a.ldwlab = ldw;
+  return gemm2::launch<gemm2::kLCEdX, true>(E, W, dX, nullptr, M, N, V, lde, ldw, ldd, 0, 0, 0, 0, nullptr, nullptr, st,
+                                             gemm2::ASplit(), a);
 }

@@ -199,3 +199,166 @@ ODB_EXPORT int odb_ce_fwd(const void* logits, const void* labels, int rows, int 
   ODB_CHECK_LAST();
   return 0;
 }
+
+// =============================================================================================== fused linear-cross-entropy
+// Host-free bookkeeping + the two thin passes around the LCE GEMMs of gemm2_sm100.cu (kLCEFwd / kLCEdX):
+//
+//   lce_prep       labels -> HF-shifted labels (position s predicts token s+1, last position ignored), n_valid,
+//                  gscale = loss_scale / max(n_valid, 1), loss_sum = 0             (replaces eight ATen launches)
+//   lce_label_dot  c[t] = x[t] . W[label[t]] + 40  (fp32)  - the shift of the exponentials, known BEFORE the GEMM, which is
+//                  what lets the GEMM epilogue emit exp(z - c) directly instead of logits: the label term of
+//                  sum_v exp(z_v - c) is exp(-40), so the row sum can never underflow, and loss_t = log(sum) + 40
+//   lce_finalize   per row: S = sum of the partial planes ; loss += log S ; rowscale = gscale / S ;
+//                  xs[t] = bf16(rowscale * x[t])   (B operand of the dW GEMM: dW = E^T xs - scatter)
+//                  dW[label[t]] -= gscale * x[t]   (the one-hot term of softmax - onehot, a vector red.add per row)
+// The shift is placed kLceShiftOffset nats ABOVE the label logit: the fp32 row sum then has head-room for best logits up to
+// ~69 + 40 = 109 nats above the label (the GEMM epilogue clamps the exponent at 2^100), while the label term itself,
+// exp(-40) = 4e-18, keeps the sum far from underflow.  loss_t = log(sum_v exp(z_v - c_t)) + kLceShiftOffset.
+constexpr float kLceShiftOffset = 40.f;
+
+__global__ void __launch_bounds__(1024) lce_prep_kernel(const long long* __restrict__ src, long long* __restrict__ dst, int B, int S,
+                                                        float loss_scale, float* __restrict__ n_valid,
+                                                        float* __restrict__ gscale, float* __restrict__ loss_sum) {
+  __shared__ float sm[33];
+  const int T = B * S;
+  float cnt = 0.f;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const int s = t % S;
+    const long long y = (s == S - 1) ? -100 : src[t + 1];
+    dst[t] = y;
+    cnt += (y >= 0) ? 1.f : 0.f;
+  }
+  cnt = block_sum(cnt, sm);
+  if (threadIdx.x == 0) {
+    const float nv = fmaxf(cnt, 1.f);
+    *n_valid = nv;
+    *gscale = loss_scale / nv;
+    *loss_sum = 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256) lce_label_dot_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                            const __nv_bfloat16* __restrict__ W, long long ldw,
+                                                            const long long* __restrict__ labels, float* __restrict__ c,
+                                                            int T, int h) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < T; t += gridDim.x * wpb) {
+    const long long y = labels[t];
+    float acc = 0.f;
+    if (y >= 0) {
+      const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)t * ldx);
+      const uint4* wr = reinterpret_cast<const uint4*>(W + (size_t)y * ldw);
+      for (int k = lane; k < h / 8; k += 32) {
+        float a[8], b[8];
+        unpack8(ld_nc_v4(xr + k), a);
+        unpack8(ld_nc_v4(wr + k), b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc = fmaf(a[j], b[j], acc);
+      }
+      acc = warp_sum(acc);
+    }
+    if (lane == 0) c[t] = (y >= 0) ? acc + kLceShiftOffset : 0.f;
+  }
+}
+
+constexpr int LCE_FIN_ROWS = 64;       // rows per CTA of lce_finalize (256 threads: 4 plane-slices x 64 rows, then 8 warps x 8 rows)
+
+__global__ void __launch_bounds__(256) lce_finalize_kernel(const float* __restrict__ partials, int planes, int T,
+                                                           const long long* __restrict__ labels,
+                                                           const float* __restrict__ gscale_ptr, float* __restrict__ loss_sum,
+                                                           float* __restrict__ sumsq_out, float* __restrict__ rowscale,
+                                                           const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                           __nv_bfloat16* __restrict__ xs, long long ldxs,
+                                                           float* __restrict__ dW, long long lddw, int h) {
+  __shared__ float s_part[4][LCE_FIN_ROWS];
+  __shared__ float s_sq[4][LCE_FIN_ROWS];
+  __shared__ float s_scale[LCE_FIN_ROWS];
+  __shared__ float sm[33];
+  const int r = threadIdx.x & (LCE_FIN_ROWS - 1), q = threadIdx.x >> 6;
+  const int t0 = blockIdx.x * LCE_FIN_ROWS;
+  const int t = t0 + r;
+  float s = 0.f, sq = 0.f;
+  if (t < T) {
+#pragma unroll 4
+    for (int pl = q; pl < planes; pl += 4) s += partials[(size_t)pl * T + t];       // coalesced over the 64 rows
+    if (sumsq_out) {
+#pragma unroll 4
+      for (int pl = q; pl < planes; pl += 4) sq += partials[(size_t)(planes + pl) * T + t];
+    }
+  }
+  s_part[q][r] = s;
+  s_sq[q][r] = sq;
+  __syncthreads();
+  const float gscale = *gscale_ptr;
+  float loss = 0.f, sqsum = 0.f;
+  if (q == 0) {
+    const float S = s_part[0][r] + s_part[1][r] + s_part[2][r] + s_part[3][r];
+    const bool valid = (t < T) && labels[t] >= 0;
+    loss = valid ? __logf(S) + kLceShiftOffset : 0.f;
+    const float rs = valid ? gscale / S : 0.f;
+    s_scale[r] = rs;
+    if (t < T && rowscale) rowscale[t] = rs;
+    sqsum = s_sq[0][r] + s_sq[1][r] + s_sq[2][r] + s_sq[3][r];
+  }
+  loss = block_sum(loss, sm);                            // also orders s_scale for the second phase
+  if (threadIdx.x == 0) atomicAdd(loss_sum, loss);
+  if (sumsq_out) {
+    sqsum = block_sum(sqsum, sm);
+    if (threadIdx.x == 0) atomicAdd(sumsq_out, sqsum);
+  }
+  if (!xs) return;                                       // evaluation: loss only
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int rr = warp; rr < LCE_FIN_ROWS; rr += 8) {
+    const int tt = t0 + rr;
+    if (tt >= T) break;
+    const float rs = s_scale[rr];
+    const long long y = labels[tt];
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)tt * ldx);
+    uint4* xo = reinterpret_cast<uint4*>(xs + (size_t)tt * ldxs);
+    float* dwr = (y >= 0 && dW) ? dW + (size_t)y * lddw : nullptr;
+    for (int k = lane; k < h / 8; k += 32) {
+      float f[8], o[8];
+      unpack8(ld_nc_v4(xr + k), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = f[j] * rs;
+      st_na_v4(xo + k, pack8(o));
+      if (dwr) {
+        red_add_f4(dwr + k * 8, make_float4(-gscale * f[0], -gscale * f[1], -gscale * f[2], -gscale * f[3]));
+        red_add_f4(dwr + k * 8 + 4, make_float4(-gscale * f[4], -gscale * f[5], -gscale * f[6], -gscale * f[7]));
+      }
+    }
+  }
+}
+
+ODB_EXPORT int odb_lce_prep(const void* labels_in, void* labels_out, int B, int S, float loss_scale, void* n_valid, void* gscale,
+                            void* loss_sum, cudaStream_t st) {
+  if (B <= 0 || S <= 0) return -1;
+  lce_prep_kernel<<<1, 1024, 0, st>>>((const long long*)labels_in, (long long*)labels_out, B, S, loss_scale, (float*)n_valid,
+                                      (float*)gscale, (float*)loss_sum);
+  ODB_CHECK_LAST();
+  return 0;
+}
+
+ODB_EXPORT int odb_lce_label_dot(const void* x, long long ldx, const void* W, long long ldw, const void* labels, void* c, int T,
+                                 int h, cudaStream_t st) {
+  if (h % 8 || ldx % 8 || ldw % 8) return -1;
+  const int blocks = ceil_div(T, 8) < 148 * 8 ? ceil_div(T, 8) : 148 * 8;
+  lce_label_dot_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)W, ldw,
+                                               (const long long*)labels, (float*)c, T, h);
+  ODB_CHECK_LAST();
+  return 0;
+}
+
+// xs / dW / rowscale / sumsq may be null (evaluation: only the loss is produced)
+ODB_EXPORT int odb_lce_finalize(const void* partials, int planes, int T, const void* labels, const void* gscale, void* loss_sum,
+                                void* sumsq, void* rowscale, const void* x, long long ldx, void* xs, long long ldxs, void* dW,
+                                long long lddw, int h, cudaStream_t st) {
+  if (h % 8 || ldx % 8 || ldxs % 8 || lddw % 4) return -1;
+  lce_finalize_kernel<<<ceil_div(T, LCE_FIN_ROWS), 256, 0, st>>>((const float*)partials, planes, T, (const long long*)labels,
+                                                                 (const float*)gscale, (float*)loss_sum, (float*)sumsq,
+                                                                 (float*)rowscale, (const __nv_bfloat16*)x, ldx,
+                                                                 (__nv_bfloat16*)xs, ldxs, (float*)dW, lddw, h);
+  ODB_CHECK_LAST();
+  return 0;
+}

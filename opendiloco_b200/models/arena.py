@@ -4,6 +4,9 @@
   shadow  bf16 [P]   - compute weights read by the GEMMs (re-written by the fused AdamW / outer kernels)
   grad    fp32 [P]   - gradient accumulator (wgrad GEMMs accumulate straight into it)
 
+There is no transposed copy of the weights: the dgrad GEMMs read ``shadow`` in its forward [out, in] layout as an MN-major
+tcgen05 operand (``ops.tc_gemm.linear_nn``).
+
 One buffer => one fused optimizer launch, one collective per outer step (the reference sends 111 per-tensor
 messages: train_diloco_torch.py:342-346), and q|k|v / gate|up weights that are physically
 adjacent so a single GEMM covers them.  ``nn.Parameter`` objects handed to user code are *views* into ``master`` with
@@ -79,8 +82,6 @@ class ParamArena:
                 off += n
         self.used = off
         self.numel = (off + TOTAL_ALIGN - 1) // TOTAL_ALIGN * TOTAL_ALIGN
-        self.shadow_t: torch.Tensor | None = None     # transposed bf16 weights for dgrad (CUDA bf16 only)
-        self.shadow_dirty = True                      # set whenever `shadow` is rewritten (optimizer / outer step / load)
         self._alloc(torch.device(device))
 
     # ------------------------------------------------------------------ storage
@@ -107,37 +108,8 @@ class ParamArena:
         if self.shadow is self.master:
             self.shadow = buf
         self.master = buf
-        self.shadow_dirty = True
-
-    # ------------------------------------------------------------------ transposed weights (dgrad as a K-major GEMM)
-    def _t_groups(self):
-        """(first tensor name, rows, cols) of every matrix that takes part in a dgrad."""
-        c = self.cfg
-        out = [("lm_head.weight", c.vocab_size, c.hidden_size)]
-        for l in range(c.num_hidden_layers):
-            p = f"model.layers.{l}."
-            out += [(p + "self_attn.q_proj.weight", c.qkv_dim, c.hidden_size), (p + "self_attn.o_proj.weight", c.hidden_size, c.q_dim),
-                    (p + "mlp.gate_proj.weight", 2 * c.intermediate_size, c.hidden_size),
-                    (p + "mlp.down_proj.weight", c.hidden_size, c.intermediate_size)]
-        return out
-
-    def wT(self, first: str, rows: int, cols: int) -> torch.Tensor | None:
-        """W^T ([cols, rows], row-major bf16) of the matrix starting at slot ``first``; None off the CUDA-bf16 path."""
-        if not (self.device.type == "cuda" and self.compute_dtype == torch.bfloat16):
-            return None
-        if self.shadow_t is None:
-            self.shadow_t = torch.empty(self.numel, dtype=torch.bfloat16, device=self.device)
-            self.shadow_dirty = True
-        if self.shadow_dirty:
-            for name, r, c in self._t_groups():
-                o = self.slots[name].offset
-                self.shadow_t[o:o + r * c].view(c, r).copy_(self.shadow[o:o + r * c].view(r, c).t())
-            self.shadow_dirty = False
-        o = self.slots[first].offset
-        return self.shadow_t[o:o + rows * cols].view(cols, rows)
 
     def sync_shadow(self) -> None:
-        self.shadow_dirty = True
         if self.shadow is not self.master:
             if self.shadow.dtype == torch.bfloat16:
                 K.cast_to_bf16(self.master, self.shadow)

@@ -50,7 +50,8 @@ class _Workspace:
         f32 = torch.float32
         self.B, self.S, self.T = B, S, T
         self.ids = torch.empty(T, dtype=torch.int64, device=device)
-        self.labels = torch.empty(T, dtype=torch.int64, device=device)
+        self.labels = torch.empty(T, dtype=torch.int64, device=device)      # HF-shifted labels
+        self.labels_in = torch.empty(T, dtype=torch.int64, device=device)   # staging for host / strided label tensors
         # saved per layer
         self.xa = [e(T, h) for _ in range(L)]         # residual stream entering the attention block
         self.rstd1 = [e(T, dt=f32) for _ in range(L)]
@@ -74,12 +75,30 @@ class _Workspace:
         self.dqkv = e(T, cfg.qkv_dim)
         self.dact = e(T, i)
         self.dxnf = e(T, h)
-        self.logits = e(min(lce_chunk, T), cfg.vocab_size)
+        self.lce_rows = min(lce_chunk, T)
+        self._dev, self._dt, self._V = device, dtype, cfg.vocab_size
+        self._logits = None          # reference path only (CPU / fp32 / fp16): bf16 kernels never materialise logits
+        self._lce = None             # fused LCE buffers, allocated on first use
         self.loss_sum = torch.zeros(1, dtype=f32, device=device)
         self.gscale = torch.ones(1, dtype=f32, device=device)
         self.n_valid = torch.ones(1, dtype=f32, device=device)
         self.sumsq = torch.zeros(1, dtype=f32, device=device)
         self.cos, self.sin = K.rope_tables(S, cfg.head_dim, cfg.rope_theta, device)
+
+    @property
+    def logits(self) -> torch.Tensor:
+        if self._logits is None:
+            self._logits = torch.empty(self.lce_rows, self._V, dtype=self._dt, device=self._dev)
+        return self._logits
+
+    def lce_buffers(self, planes: int, h: int):
+        """(shift [T], rowscale [T], partials [2*planes, C], e [C, V] bf16, xs [C, h] bf16) of the fused LCE."""
+        if self._lce is None:
+            C, f32 = self.lce_rows, torch.float32
+            mk = lambda *shape, dt: torch.empty(*shape, dtype=dt, device=self._dev)  # noqa: E731
+            self._lce = (mk(self.T, dt=f32), mk(self.T, dt=f32), mk(2 * planes * C, dt=f32), mk(C, self._V, dt=self._dt),
+                         mk(C, h, dt=self._dt))
+        return self._lce
 
 
 class LlamaEngine:
@@ -155,31 +174,30 @@ class LlamaEngine:
     # --------------------------------------------------------------------------------------------- LM head + loss
     def head_loss(self, ws: _Workspace, labels: torch.Tensor | None, loss_scale: float, with_grad: bool,
                   direct: bool) -> torch.Tensor:
-        """Chunked linear-cross-entropy.  Returns the mean loss (0-dim fp32 tensor on device).
+        """Linear-cross-entropy of the LM head.  Returns the mean loss (0-dim fp32 tensor on device).
 
         with_grad: also produce d(xnf) in ws.dxnf and the lm_head weight gradient, scaled by loss_scale / n_valid.
         direct: accumulate the lm_head gradient into the arena now (scale known); otherwise into ``head_grad_tmp`` so
         that autograd can apply the upstream gradient later.
+
+        CUDA bf16: the fused path (``_head_loss_fused``) - logits never exist.  Other dtypes / CPU: the reference path
+        that materialises a logits tile per chunk (same math, PyTorch ops).
+        Reference call site: train_diloco_torch.py:313-314 / train_fsdp.py:378-379 -> loss_utils.py:45-67.
         """
         cfg, ar = self.cfg, self.arena
-        T, V = ws.T, cfg.vocab_size
-        B, S = ws.B, ws.S
+        V = cfg.vocab_size
         # HF shift: position s predicts token s+1 ; last position of every sequence is ignored
-        lab = ws.labels.view(B, S)
-        src = labels.reshape(B, S)
-        lab[:, : S - 1].copy_(src[:, 1:], non_blocking=True)
-        lab[:, S - 1].fill_(IGNORE_INDEX)
-        ws.n_valid.copy_((ws.labels != IGNORE_INDEX).sum().to(torch.float32).reshape(1))
-        ws.n_valid.clamp_(min=1.0)
-        torch.reciprocal(ws.n_valid, out=ws.gscale)
-        ws.gscale.mul_(float(loss_scale))
-        ws.loss_sum.zero_()
+        src = labels.reshape(-1)
+        if src.device != ws.labels.device or src.dtype != torch.int64 or not src.is_contiguous():
+            ws.labels_in.copy_(src, non_blocking=True)
+            src = ws.labels_in
+        K.lce_prep(src, ws.labels, ws.B, ws.S, loss_scale, ws.n_valid, ws.gscale, ws.loss_sum)
         w_lm = ar.w("lm_head.weight")
-        w_lm_t = ar.wT("lm_head.weight", V, cfg.hidden_size) if with_grad else None
         hooked = self.module_hooks.get("lm_head")
         want_norm = self.collect_act_norms or (hooked is not None and bool(hooked._forward_hooks))
         if want_norm:
             ws.sumsq.zero_()
+        g_lm = None
         if with_grad:
             if direct:
                 g_lm = ar.g("lm_head.weight")
@@ -189,19 +207,10 @@ class LlamaEngine:
                 else:
                     self.head_grad_tmp.zero_()
                 g_lm = self.head_grad_tmp
-        C = ws.logits.shape[0]
-        for c0 in range(0, T, C):
-            c1 = min(T, c0 + C)
-            logits = ws.logits[: c1 - c0]
-            G.mm_nt(ws.xnf[c0:c1], w_lm, out=logits)
-            if with_grad:
-                K.ce_fwd_bwd_(logits, ws.labels[c0:c1], ws.gscale, ws.loss_sum, ws.sumsq if want_norm else None)
-                G.mm_nn(logits, w_lm, out=ws.dxnf[c0:c1], b_t=w_lm_t)
-                G.mm_tn_acc(logits, ws.xnf[c0:c1], g_lm)
-            else:
-                if want_norm:
-                    ws.sumsq.add_(logits.float().pow(2).sum())
-                K.ce_fwd(logits, ws.labels[c0:c1], ws.loss_sum)
+        if TC.lce_usable(ws.xnf, w_lm) and os.environ.get("ODB_LCE_FUSED", "1") != "0":
+            self._head_loss_fused(ws, w_lm, g_lm, want_norm)
+        else:
+            self._head_loss_reference(ws, w_lm, g_lm, want_norm)
         if want_norm:
             nrm = ws.sumsq.sqrt()[0]
             if self.collect_act_norms:
@@ -209,6 +218,54 @@ class LlamaEngine:
             if hooked is not None and hooked._forward_hooks:
                 self._fire_hooks("lm_head", _NormOnly(nrm))
         return (ws.loss_sum / ws.n_valid)[0]
+
+    def _head_loss_fused(self, ws: _Workspace, w_lm: torch.Tensor, g_lm: torch.Tensor | None, want_norm: bool) -> None:
+        """Fused linear-cross-entropy on tcgen05.  Per chunk of rows:
+
+          c_t   = x_t . W[y_t]                               (lce_label_dot: the label logit, 2 x T x h bytes)
+          E     = exp(X W^T - c)   + partial row sums        (ONE GEMM, epilogue in registers; bf16 E only when training)
+          S_t, loss_t = log S_t, rowscale_t = gscale / S_t, xs = rowscale * x, dW[y_t] -= gscale x_t     (lce_finalize)
+          dX    = rowscale * (E W) - gscale W[y]             (dgrad GEMM, W read MN-major, normaliser + one-hot in the epilogue)
+          dW   += E^T xs                                     (weight-gradient GEMM)
+
+        softmax - onehot is never formed and there is no pass over a [T, V] tensor outside the three GEMMs: the shift c is
+        known before the GEMM, so the exponentials can be emitted by its epilogue, and the per-row normaliser moves to
+        the fp32 side of the two gradient GEMMs.  In evaluation (g_lm is None) nothing of size [T, V] is written at all.
+        """
+        T, h = ws.T, self.cfg.hidden_size
+        V = w_lm.shape[0]
+        planes = TC.lce_planes(V)
+        shift, rowscale, partials, e_buf, xs_buf = ws.lce_buffers(planes, h)
+        train = g_lm is not None
+        K.lce_label_dot(ws.xnf, w_lm, ws.labels, shift)
+        C = ws.lce_rows
+        for c0 in range(0, T, C):
+            c1 = min(T, c0 + C)
+            n = c1 - c0
+            x = ws.xnf[c0:c1]
+            e = e_buf[:n] if train else None
+            TC.lce_fwd(x, w_lm, shift[c0:c1], partials, e, want_sumsq=want_norm)
+            K.lce_finalize(partials, planes, ws.labels[c0:c1], ws.gscale, ws.loss_sum, ws.sumsq if want_norm else None,
+                           rowscale[c0:c1] if train else None, x, xs_buf[:n] if train else None, g_lm)
+            if train:
+                TC.lce_dx(e, w_lm, rowscale[c0:c1], ws.labels[c0:c1], ws.gscale, ws.dxnf[c0:c1])
+                G.mm_tn_acc(e, xs_buf[:n], g_lm)
+
+    def _head_loss_reference(self, ws: _Workspace, w_lm: torch.Tensor, g_lm: torch.Tensor | None, want_norm: bool) -> None:
+        T = ws.T
+        C = ws.lce_rows
+        for c0 in range(0, T, C):
+            c1 = min(T, c0 + C)
+            logits = ws.logits[: c1 - c0]
+            G.mm_nt(ws.xnf[c0:c1], w_lm, out=logits)
+            if g_lm is not None:
+                K.ce_fwd_bwd_(logits, ws.labels[c0:c1], ws.gscale, ws.loss_sum, ws.sumsq if want_norm else None)
+                G.mm_nn(logits, w_lm, out=ws.dxnf[c0:c1])
+                G.mm_tn_acc(logits, ws.xnf[c0:c1], g_lm)
+            else:
+                if want_norm:
+                    ws.sumsq.add_(logits.float().pow(2).sum())
+                K.ce_fwd(logits, ws.labels[c0:c1], ws.loss_sum)
 
     def logits(self, ws: _Workspace) -> torch.Tensor:
         """Materialise full logits [T, V] (inference / debugging only)."""
@@ -226,21 +283,21 @@ class LlamaEngine:
             p = f"model.layers.{l}."
             # ---- MLP block (ws.dx is the gradient of x_out = xm + down(act))
             G.mm_tn_acc(ws.dx, ws.act[l], ar.g(p + "mlp.down_proj.weight"))
-            wT_down = ar.wT(p + "mlp.down_proj.weight", h, i)
-            if TC.swiglu_bwd_usable(ws.dx, wT_down, ws.gu[l]):
-                TC.linear_swiglu_bwd(ws.dx, wT_down, ws.gu[l])             # dgrad GEMM with the SwiGLU backward as epilogue
+            w_down = ar.w(p + "mlp.down_proj.weight")
+            if TC.swiglu_bwd_usable(ws.dx, w_down, ws.gu[l]):
+                TC.linear_swiglu_bwd(ws.dx, w_down, ws.gu[l])              # dgrad GEMM with the SwiGLU backward as epilogue
             else:
-                G.mm_nn(ws.dx, ar.w(p + "mlp.down_proj.weight"), out=ws.dact, b_t=wT_down)
+                G.mm_nn(ws.dx, w_down, out=ws.dact)
                 K.swiglu_bwd(ws.dact, ws.gu[l], ws.gu[l])                  # in place: gu <- d(gu)
             G.mm_tn_acc(ws.gu[l], ws.xn2[l], ar.gu_g(l))
-            G.mm_nn(ws.gu[l], ar.gu_w(l), out=ws.dn, b_t=ar.wT(p + "mlp.gate_proj.weight", 2 * i, h))
+            G.mm_nn(ws.gu[l], ar.gu_w(l), out=ws.dn)
             K.rmsnorm_bwd(ws.dn, ws.xm[l], ar.w(p + "post_attention_layernorm.weight"), ws.rstd2[l], ws.dx, ws.dx,
                           ar.g(p + "post_attention_layernorm.weight"))
             # ---- attention block (ws.dx is now the gradient of xm = xa + o(att))
             G.mm_tn_acc(ws.dx, ws.att[l], ar.g(p + "self_attn.o_proj.weight"))
-            G.mm_nn(ws.dx, ar.w(p + "self_attn.o_proj.weight"), out=ws.datt, b_t=ar.wT(p + "self_attn.o_proj.weight", h, cfg.q_dim))
-            wT_qkv = ar.wT(p + "self_attn.q_proj.weight", cfg.qkv_dim, h)
-            parts_ok = attention_mask is None and wT_qkv is not None and cfg.q_dim % 64 == 0 and cfg.kv_dim % 64 == 0
+            G.mm_nn(ws.dx, ar.w(p + "self_attn.o_proj.weight"), out=ws.datt)
+            parts_ok = (attention_mask is None and cfg.q_dim % 64 == 0 and cfg.kv_dim % 64 == 0
+                        and TC.nn_usable(ws.datt, ar.qkv_w(l)))
             if attention_mask is None:
                 res = A.attention_bwd(ws.datt, ws.qkv[l], ws.att[l], ws.aux[l], ws.dqkv, B, S, Hq, Hkv, D, want_parts=parts_ok,
                                       rope=(ws.cos, ws.sin))
@@ -260,12 +317,12 @@ class LlamaEngine:
                     G.mm_tn_acc(dq, ws.xn1[l], gq[: cfg.q_dim])
                     G.mm_tn_acc(dk, ws.xn1[l], gq[cfg.q_dim: cfg.q_dim + cfg.kv_dim])
                     G.mm_tn_acc(dv, ws.xn1[l], gq[cfg.q_dim + cfg.kv_dim:])
-                TC.linear_a3(dq, dk, dv, wT_qkv, ws.dn)
+                TC.linear_nn_a3(dq, dk, dv, ar.qkv_w(l), ws.dn)
             else:
                 if attention_mask is not None or not A.bwd_applies_rope(ws.aux[l]):
                     K.rope_(ws.dqkv, ws.cos, ws.sin, S, Hq + Hkv, D, backward=True)
                 G.mm_tn_acc(ws.dqkv, ws.xn1[l], ar.qkv_g(l))
-                G.mm_nn(ws.dqkv, ar.qkv_w(l), out=ws.dn, b_t=wT_qkv)
+                G.mm_nn(ws.dqkv, ar.qkv_w(l), out=ws.dn)
             K.rmsnorm_bwd(ws.dn, ws.xa[l], ar.w(p + "input_layernorm.weight"), ws.rstd1[l], ws.dx, ws.dx,
                           ar.g(p + "input_layernorm.weight"))
             ws.att[l] = None

@@ -6,9 +6,10 @@ Three shapes of GEMM appear in a Llama step:
   * ``mm_nn``      y[M,K]  = a[M,N] @ b[N,K]            dgrad                 (b is N-major)
   * ``mm_tn_acc``  w[N,K] += a[T,N]^T @ b[T,K]  (fp32)  wgrad, accumulated straight into the fp32 gradient arena
 
-Plain (un-fused) GEMMs go to cuBLASLt through ``torch.mm(out=...)``; the fused hot ops (QKV+RoPE, gate|up+SwiGLU,
-LM-head+CE) use the tcgen05 kernels in ``csrc/gemm_sm100.cu`` via :mod:`opendiloco_b200.ops.tc_gemm` when the
-operand shapes qualify.
+CUDA bf16 operands always run on the tcgen05 kernels of ``csrc/gemm2_sm100.cu`` / ``gemm_sm100.cu`` /
+``wgrad_sm100.cu`` (:mod:`opendiloco_b200.ops.tc_gemm`): ``mm_nt`` with K-major operands, ``mm_nn`` with the weight read
+as an MN-major B operand (no transposed copy), ``mm_tn_acc`` with both operands MN-major and a TMA reduce-add epilogue.
+``torch.mm`` (cuBLAS / ATen) is only the fp32 / fp16 / CPU path and the ``ODB_TC_GEMM=0`` comparison baseline.
 """
 from __future__ import annotations
 
@@ -28,11 +29,11 @@ def mm_nt(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None) -> 
     return torch.mm(a, b.t(), out=out)
 
 
-def mm_nn(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, b_t: torch.Tensor | None = None) -> torch.Tensor:
-    """a[M,N] @ b[N,K] (dgrad).  With ``b_t`` = b^T stored row-major ([K,N]) the product is a K-major "TN" GEMM and runs
-    on the tcgen05 kernel; the arena keeps such transposed bf16 copies of the weights."""
-    if b_t is not None and TC.usable(a, b_t) and (out is None or TC.usable(out)):
-        return TC.linear(a, b_t, out)
+def mm_nn(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """a[M,N] @ b[N,K] (dgrad): the weight ``b`` stays in its forward [out, in] layout and is fed to tcgen05 as an
+    MN-major operand (UMMA descriptor LBO/SBO), so no transposed weight copy exists."""
+    if TC.nn_usable(a, b, out):
+        return TC.linear_nn(a, b, out)
     if out is None:
         return torch.mm(a, b)
     return torch.mm(a, b, out=out)

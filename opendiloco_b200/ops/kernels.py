@@ -230,6 +230,64 @@ def ce_fwd(logits: torch.Tensor, labels: torch.Tensor, loss_sum: torch.Tensor) -
         loss_sum.add_(((lse - xy) * valid).sum())
 
 
+# ------------------------------------------------------------------------------------------------ fused linear-cross-entropy helpers
+import ctypes as _ct
+
+_lib.register_optional("odb_lce_prep", [_ct.c_void_p, _ct.c_void_p, _ct.c_int, _ct.c_int, _ct.c_float, _ct.c_void_p, _ct.c_void_p,
+                                       _ct.c_void_p, _ct.c_void_p])
+_lib.register_optional("odb_lce_label_dot", [_ct.c_void_p, _ct.c_longlong, _ct.c_void_p, _ct.c_longlong, _ct.c_void_p, _ct.c_void_p,
+                                            _ct.c_int, _ct.c_int, _ct.c_void_p])
+_lib.register_optional("odb_lce_finalize", [_ct.c_void_p, _ct.c_int, _ct.c_int, _ct.c_void_p, _ct.c_void_p, _ct.c_void_p, _ct.c_void_p,
+                                           _ct.c_void_p, _ct.c_void_p, _ct.c_longlong, _ct.c_void_p, _ct.c_longlong, _ct.c_void_p,
+                                           _ct.c_longlong, _ct.c_int, _ct.c_void_p])
+
+
+def lce_prep(labels_in: torch.Tensor, labels_out: torch.Tensor, B: int, S: int, loss_scale: float, n_valid: torch.Tensor,
+             gscale: torch.Tensor, loss_sum: torch.Tensor) -> None:
+    """HF label shift (position s predicts token s+1, last position of every sequence ignored; loss_utils.py:45-67) +
+    n_valid = max(#labels >= 0, 1) + gscale = loss_scale / n_valid + loss_sum = 0, in one launch."""
+    if labels_out.is_cuda:
+        assert labels_in.dtype == torch.int64 and labels_in.is_contiguous() and labels_out.is_contiguous()
+        _lib.check(_lib.cuda_lib().odb_lce_prep(_p(labels_in), _p(labels_out), B, S, float(loss_scale), _p(n_valid), _p(gscale),
+                                                _p(loss_sum), _lib.stream_ptr(labels_out)), "lce_prep")
+        _lib.count_launch()
+        return
+    lab = labels_out.view(B, S)
+    lab[:, : S - 1].copy_(labels_in.reshape(B, S)[:, 1:])
+    lab[:, S - 1].fill_(-100)
+    n_valid.copy_((labels_out >= 0).sum().to(torch.float32).clamp(min=1.0).reshape(1))
+    gscale.copy_(float(loss_scale) / n_valid)
+    loss_sum.zero_()
+
+
+def lce_label_dot(x: torch.Tensor, w: torch.Tensor, labels: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out[t] = x[t] . w[labels[t]] + 40 in fp32 (0 for ignored rows): the shift of the exponentials of the fused LCE
+    (40 nats of head-room above the label logit, see csrc/lce.cu)."""
+    T, h = x.shape
+    if x.is_cuda and x.dtype == BF16:
+        _lib.check(_lib.cuda_lib().odb_lce_label_dot(_p(x), x.stride(0), _p(w), w.stride(0), _p(labels), _p(out), T, h,
+                                                     _lib.stream_ptr(x)), "lce_label_dot")
+        _lib.count_launch()
+    else:
+        safe = labels.clamp(min=0)
+        out.copy_(((x.float() * w.float()[safe]).sum(-1) + 40.0) * (labels >= 0))
+    return out
+
+
+def lce_finalize(partials: torch.Tensor, planes: int, labels: torch.Tensor, gscale: torch.Tensor, loss_sum: torch.Tensor,
+                 sumsq: torch.Tensor | None, rowscale: torch.Tensor | None, x: torch.Tensor, xs: torch.Tensor | None,
+                 dw: torch.Tensor | None) -> None:
+    """Row sums of the partial planes -> loss_sum += sum_t log S_t ; rowscale = gscale / S ; xs = bf16(rowscale * x) ;
+    dw[labels[t]] -= gscale * x[t] (the one-hot term of the LM-head weight gradient).  CUDA only (the CPU path of the
+    engine uses the materialising reference)."""
+    T, h = x.shape
+    _lib.check(_lib.cuda_lib().odb_lce_finalize(_p(partials), planes, T, _p(labels), _p(gscale), _p(loss_sum), _p(sumsq),
+                                                _p(rowscale), _p(x), x.stride(0), _p(xs), xs.stride(0) if xs is not None else 0,
+                                                _p(dw), dw.stride(0) if dw is not None else 0, h, _lib.stream_ptr(x)),
+               "lce_finalize")
+    _lib.count_launch()
+
+
 # ------------------------------------------------------------------------------------------------ optimizer kernels
 HP_LR, HP_B1, HP_B2, HP_EPS, HP_WD, HP_BC1, HP_BC2, HP_MAXNORM, HP_INVSCALE = range(9)
 HP_SIZE = 16

@@ -36,11 +36,6 @@ class FlatView:
         self.shard_group = None
         self.arena = getattr(params[0], "_odb_arena", None) if params else None
 
-    def mark_dirty(self) -> None:
-        """The compute weights changed: derived copies (transposed bf16 weights) must be rebuilt before their next use."""
-        if self.arena is not None:
-            self.arena.shadow_dirty = True
-
     @property
     def numel(self) -> int:
         return self.flat.numel()
@@ -66,7 +61,6 @@ class FlatView:
     def gather_compute_weights(self) -> None:
         """After a sharded update: every rank publishes its slice of the compute weights (bf16 shadow, or fp32 master
         when computing in fp32) to the worker's other GPUs."""
-        self.mark_dirty()
         if not self.sharded:
             return
         buf = self.shadow if self.shadow is not None else self.flat
@@ -108,6 +102,8 @@ class FusedAdamW(torch.optim.Optimizer):
     (reference loop order: clip, then step) hands its partial norms to the next step instead of rescaling gradients.
     """
 
+    HP_RING = 8
+
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2,
                  max_grad_norm: float | None = None, zero_grad_in_step: bool = False, dp_group=None, shard: bool = False):
         params = list(params)
@@ -130,13 +126,19 @@ class FusedAdamW(torch.optim.Optimizer):
         self.max_grad_norm = max_grad_norm
         self.zero_grad_in_step = zero_grad_in_step
         self._step = 0
-        self._hp_host = torch.zeros(K.HP_SIZE, dtype=torch.float32, pin_memory=dev.type == "cuda")
+        # per-step scalars travel through a RING of pinned slots, each guarded by an event recorded after its H2D copy: the
+        # host may run ahead of the GPU by several steps (only rank 0 reads the loss), and a single slot would be
+        # rewritten before the asynchronous copy of an earlier step has read it
+        self._hp_ring = [torch.zeros(K.HP_SIZE, dtype=torch.float32, pin_memory=dev.type == "cuda") for _ in range(self.HP_RING)]
+        self._hp_events: list = [None] * self.HP_RING
+        self._hp_slot = 0
         self._hp = torch.zeros(K.HP_SIZE, dtype=torch.float32, device=dev)
         self._partials = torch.zeros(K.MAX_PARTIALS, dtype=torch.float32, device=dev)
         self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self.stats = torch.zeros(2, dtype=torch.float32, device=dev)   # [grad_norm, clip_coef] of the last step
         self._pending: tuple[int, float] | None = None                # (n_partials, max_norm) from clip_grad_norm_
         self._grads_synced = False
+        self._inv_scale: torch.Tensor | None = None                   # 1/loss-scale handed over by unscale_()
         arena = getattr(params[0], "_odb_arena", None)
         if arena is not None:
             arena.fused_optimizer = weakref.ref(self)                 # lets model.clip_grad_norm_() find us
@@ -205,23 +207,74 @@ class FusedAdamW(torch.optim.Optimizer):
     # ----------------------------------------------------------------- clipping hand-off
     @torch.no_grad()
     def _norm_partials(self) -> int:
+        """One pass over this rank's gradients: per-CTA sums of squares + the non-finite flag (K9 / K11)."""
         fv = self.fv
+        self._flag.zero_()
         n = K.grad_sqnorm(fv.own(fv.grad), self._partials, self._flag)
         if fv.sharded:   # every shard has the same size => the same number of partials: sum them element-wise
             dist.all_reduce(self._partials[:n], op=dist.ReduceOp.SUM, group=self.dp_group)
+            dist.all_reduce(self._flag, op=dist.ReduceOp.MAX, group=self.dp_group)   # an overflow anywhere skips everywhere
         return n
 
     @torch.no_grad()
     def compute_grad_norm_partials(self, max_norm: float) -> torch.Tensor:
-        """Launch the norm pass now and remember it for the next step(); returns the (device) total norm lazily."""
+        """Launch the norm pass now and remember it for the next step(); returns the (device) total norm lazily.
+        Under a GradScaler the returned norm is that of the still-scaled gradients times 1/scale."""
         self.sync_grads()
         n = self._norm_partials()
         self._pending = (n, float(max_norm))
-        return self._partials[:n].sum().sqrt()
+        total = self._partials[:n].sum().sqrt()
+        if self._inv_scale is not None:
+            total = total * self._inv_scale
+        return total
+
+    # ----------------------------------------------------------------- GradScaler (fp16-mixed) on the kernel path
+    @torch.no_grad()
+    def unscale_(self, scaler) -> None:
+        """Stand-in for ``scaler.unscale_(optimizer)`` (train_fsdp.py:391-393): nothing is rescaled in memory - 1/scale
+        becomes the ``grad_scale_inv`` hyper-parameter of the fused step (K11 folded into K9/K10), and the non-finite
+        check is the flag of the norm pass, taken AFTER the worker-internal gradient reduction so every GPU of a worker
+        sees the same verdict."""
+        if not scaler.is_enabled():
+            return
+        if scaler._scale is None:
+            scaler._lazy_init_scale_growth_tracker(self.fv.flat.device)
+        self._inv_scale = scaler._scale.to(self.fv.flat.device, torch.float32).reciprocal()
+
+    @torch.no_grad()
+    def step_scaled(self, scaler):
+        """``scaler.step(optimizer)`` on the kernel path: unscale + inf-check + clip + AdamW in the fused launches; the
+        verdict is handed to the scaler so ``scaler.update()`` / ``found_inf_grad`` (utils.py:124-135) work unchanged."""
+        if not scaler.is_enabled():
+            return self.step()
+        from torch.amp.grad_scaler import OptState
+
+        if self._inv_scale is None:
+            self.unscale_(scaler)
+        self.step(_check_inf=True)
+        st = scaler._per_optimizer_states[id(self)]
+        st["found_inf_per_device"] = {self._flag.device: self._flag.to(torch.float32)}
+        st["stage"] = OptState.STEPPED
+        return None
 
     # ----------------------------------------------------------------- step
+    def _upload_hp(self, values: dict) -> None:
+        slot = self._hp_slot
+        self._hp_slot = (slot + 1) % self.HP_RING
+        ev = self._hp_events[slot]
+        if ev is not None:
+            ev.synchronize()                      # the copy that last read this slot has finished (normally long ago)
+        hp = self._hp_ring[slot]
+        for k, v in values.items():
+            hp[k] = v
+        self._hp.copy_(hp, non_blocking=True)
+        if self._hp.is_cuda:
+            ev = ev or torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self._hp.device))
+            self._hp_events[slot] = ev
+
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, _check_inf: bool = False):
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -236,18 +289,18 @@ class FusedAdamW(torch.optim.Optimizer):
         if self._pending is not None:
             n_part, max_norm = self._pending
             self._pending = None
-        elif max_norm is not None and max_norm > 0:
+        elif (max_norm is not None and max_norm > 0) or _check_inf:
             n_part = self._norm_partials()
-        hp = self._hp_host
-        hp[K.HP_LR] = g["lr"]
-        hp[K.HP_B1], hp[K.HP_B2], hp[K.HP_EPS], hp[K.HP_WD] = b1, b2, g["eps"], g["weight_decay"]
-        hp[K.HP_BC1] = 1.0 - b1 ** self._step
-        hp[K.HP_BC2] = 1.0 - b2 ** self._step
-        hp[K.HP_MAXNORM] = max_norm if (max_norm is not None and n_part > 0) else 0.0
-        hp[K.HP_INVSCALE] = 1.0
-        self._hp.copy_(hp, non_blocking=True)
+        self._upload_hp({K.HP_LR: g["lr"], K.HP_B1: b1, K.HP_B2: b2, K.HP_EPS: g["eps"], K.HP_WD: g["weight_decay"],
+                         K.HP_BC1: 1.0 - b1 ** self._step, K.HP_BC2: 1.0 - b2 ** self._step,
+                         K.HP_MAXNORM: max_norm if (max_norm is not None and max_norm > 0 and n_part > 0) else 0.0,
+                         K.HP_INVSCALE: 1.0})
+        if self._inv_scale is not None:           # device-side 1/scale (no host read of the GradScaler's scale)
+            self._hp[K.HP_INVSCALE:K.HP_INVSCALE + 1].copy_(self._inv_scale.reshape(1))
+            self._inv_scale = None
         K.adamw_step(fv.own(fv.flat), fv.own(fv.grad), self.exp_avg, self.exp_avg_sq, fv.own(fv.shadow), self._hp,
-                     self._partials, n_part, None, self.stats, zero_grad=self.zero_grad_in_step and not fv.sharded)
+                     self._partials, n_part, self._flag if _check_inf else None, self.stats,
+                     zero_grad=self.zero_grad_in_step and not fv.sharded)
         fv.gather_compute_weights()
         if self.zero_grad_in_step and fv.sharded:
             fv.grad.zero_()

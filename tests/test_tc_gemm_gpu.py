@@ -101,13 +101,41 @@ def test_swiglu_backward_epilogue(M, I, Kd):
     dy = torch.randn(M, Kd, device="cuda").to(BF)
     w_t = (torch.randn(I, Kd, device="cuda") * 0.1).to(BF)              # down_proj.weight^T: [I, hidden]
     gu = torch.randn(M, 2 * I, device="cuda").to(BF)
-    assert T.swiglu_bwd_usable(dy, w_t, gu)
+    w = w_t.t().contiguous()                                             # down_proj.weight as stored: [hidden, I]
+    assert T.swiglu_bwd_usable(dy, w, gu)
     dact = T.linear(dy, w_t)
     ref_unfused = K.swiglu_bwd(dact, gu)
     g, u, d = gu[:, :I].float(), gu[:, I:].float(), dy.float() @ w_t.float().t()
     sg = torch.sigmoid(g)
     ref = torch.cat([d * u * sg * (1 + g * (1 - sg)), d * g * sg], dim=1)
     fused = gu.clone()
-    T.linear_swiglu_bwd(dy, w_t, fused)
+    T.linear_swiglu_bwd(dy, w, fused)                                    # weight read MN-major in its forward layout
     assert rel(fused, ref) < 6e-3
     assert rel(fused, ref_unfused) < 2e-3                                # same bf16-rounded d(act), fast-math divide differs
+    fused_t = gu.clone()
+    T.linear_swiglu_bwd_t(dy, w_t, fused_t)                              # K-major B variant: same MMAs, same result
+    assert torch.equal(fused, fused_t)
+
+
+@pytest.mark.parametrize("M,N,Kd", [(128, 256, 64), (300, 520, 200), (1000, 136, 72), (4096, 1024, 1024), (20000, 1024, 2688),
+                                    (8192, 1024, 32000)])
+def test_linear_nn_mn_major_b(M, N, Kd):
+    """dgrad form: out = a @ b with b [K, N] row-major, fed to tcgen05 as an MN-major operand (no transposed copy)."""
+    torch.manual_seed(6)
+    a = torch.randn(M, Kd, device="cuda").to(BF)
+    b = (torch.randn(Kd, N, device="cuda") * 0.1).to(BF)
+    assert T.nn_usable(a, b)
+    out = T.linear_nn(a, b)
+    assert rel(out, a.float() @ b.float()) < 4e-3
+    assert torch.equal(out, torch.mm(a, b))               # same fp32 accumulation + single rounding as cuBLAS
+
+
+def test_linear_nn_a3_and_views():
+    torch.manual_seed(7)
+    M, N = 3000, 512
+    big = torch.randn(M, 1024, device="cuda").to(BF)
+    dq, dk, dv = big[:, :512], big[:, 512:768], big[:, 768:]
+    w = (torch.randn(1024, N, device="cuda") * 0.1).to(BF)
+    out = torch.empty(M, N, device="cuda", dtype=BF)
+    T.linear_nn_a3(dq, dk, dv, w, out)
+    assert torch.equal(out, torch.mm(big, w))
