@@ -88,6 +88,24 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
   return v;
 }
 
+// Cross-GPU waits are bounded by WALL CLOCK (globaltimer): a peer that never arrives raises the timeout flag after
+// g_outer_timeout_ns (default 20 s, odb_outer_set_timeout_ms) and the kernel returns without touching any state that the
+// missing data would have fed - the host polls the flag (FusedOuterStep.poll_timeout) and raises.
+__device__ unsigned long long g_outer_timeout_ns = 20000000000ull;
+
+__device__ __forceinline__ bool spin_until_ge(const unsigned* p, unsigned seq, int* timeout_flag) {
+  if (ld_acquire_sys(p) >= seq) return true;
+  const unsigned long long t0 = globaltimer_ns();
+  unsigned spins = 0;
+  while (ld_acquire_sys(p) < seq) {
+    if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > g_outer_timeout_ns) {
+      atomicExch(timeout_flag, 1);
+      return false;
+    }
+  }
+  return true;
+}
+
 // grid barrier (cooperative) + all-ranks barrier through the flag window.  flags[p][slot*kMaxPeers + r] on rank p is
 // written by rank r.  `seq` increases monotonically across launches so flags never need resetting.
 __device__ __forceinline__ void world_barrier(cg::grid_group& grid, const PeerPtrs& flag_ptrs, int rank, int world,
@@ -99,13 +117,7 @@ __device__ __forceinline__ void world_barrier(cg::grid_group& grid, const PeerPt
     unsigned* remote = reinterpret_cast<unsigned*>(flag_ptrs.p[peer]) + slot * kMaxPeers + rank;
     st_release_sys(remote, seq);
     const unsigned* mine = reinterpret_cast<const unsigned*>(flag_ptrs.p[rank]) + slot * kMaxPeers + peer;
-    long long spins = 0;
-    while (ld_acquire_sys(mine) < seq) {
-      if (++spins > (1ll << 31)) {   // ~tens of seconds: a peer is gone; fail loudly instead of hanging the GPU
-        atomicExch(timeout_flag, 1);
-        break;
-      }
-    }
+    spin_until_ge(mine, seq, timeout_flag);      // a peer is gone: flag it instead of hanging the GPU
   }
   grid.sync();
   __threadfence_system();
@@ -139,6 +151,7 @@ __global__ void __launch_bounds__(512) fused_outer_kernel(float* __restrict__ th
   }
   if (stamp) stamps[1] = globaltimer_ns();
   world_barrier(grid, flag_ptrs, rank, world, seq, 0, timeout_flag);
+  if (*reinterpret_cast<volatile int*>(timeout_flag)) return;      // a peer never arrived: leave theta / momentum untouched
   if (stamp) stamps[2] = globaltimer_ns();
 
   // ---------------- phase 1: reduce my slice across ranks, publish the mean to every rank
@@ -216,6 +229,7 @@ __global__ void __launch_bounds__(512) fused_outer_kernel(float* __restrict__ th
   }
   if (stamp) stamps[3] = globaltimer_ns();
   world_barrier(grid, flag_ptrs, rank, world, seq + 1, 1, timeout_flag);
+  if (*reinterpret_cast<volatile int*>(timeout_flag)) return;      // window only partially averaged: do not apply it
   if (stamp) stamps[4] = globaltimer_ns();
 
   // ---------------- phase 2: SGD-Nesterov on the whole vector from the (now averaged) local window
@@ -270,12 +284,7 @@ struct PipeCounters {            // device memory, zero-initialised once, monoto
 __device__ __forceinline__ bool wait_flags(const unsigned* base, int world, unsigned seq, int* timeout_flag) {
   // one thread per peer polls; returns false on timeout
   bool ok = true;
-  if (threadIdx.x < world) {
-    long long spins = 0;
-    while (ld_acquire_sys(base + threadIdx.x) < seq) {
-      if (++spins > (1ll << 30)) { atomicExch(timeout_flag, 1); ok = false; break; }
-    }
-  }
+  if (threadIdx.x < world) ok = spin_until_ge(base + threadIdx.x, seq, timeout_flag);
   return __syncthreads_and(ok);
 }
 
@@ -406,6 +415,154 @@ __global__ void __launch_bounds__(512) fused_outer_pipelined_kernel(
       }
     }
   }
+}
+
+// =====================================================================================================================
+// Sharded in-place version (fp32, multimem): the outer optimizer is ZeRO-1 over the swarm and the all-reduce runs on the
+// MASTER WEIGHTS themselves, which live in the symmetric window:
+//
+//     mean_local = (1/N) multimem.ld_reduce(theta_local[i])        i in MY slab           (in-switch reduction)
+//     d = theta_outer[i] - mean_local ; buf[i] = mu buf[i] + d ; theta_outer[i] -= lr (d + mu buf[i])      (my slab only)
+//     multimem.st(theta_local[i] <- theta_outer[i])                                  (switch multicast, every rank)
+//     every rank: shadow[j] = bf16(theta_local[j]) ; theta_outer[j] = theta_local[j]  for the slabs it does not own
+//
+// mean_p(theta_outer - theta_local_p) = theta_outer - mean_p(theta_local_p), so no pseudo-gradient is ever materialised:
+// there is no pre-pass, the NVLink phase starts with the kernel, the momentum is read and written by its owner only
+// (4 B/param/N instead of 8 B/param on every rank) and the only full-vector pass left is the bf16 shadow refresh.  HBM
+// traffic per rank ~18 B/param (was 46 with the replicated update), NVLink traffic unchanged (4 B/param each way).
+// The owner's momentum slab is re-replicated to the peers in the background by the host (one NCCL all-gather on a side
+// stream that overlaps the next inner steps), so checkpoints / elastic rounds still see the full outer-optimizer state.
+//
+// Rank r owns the contiguous slab r (n/N elements); a slab is cut into nchunk chunks and the comm CTAs publish
+// done[c] when chunk c of THEIR slab is on every rank; the post CTAs process chunk c of all N slabs once every rank has
+// published done[c].  Entry barrier: every rank raises ready[0] when its kernel starts (stream order: its last AdamW step
+// is complete), and nobody reduces before all N have.
+template <int kDummy>
+__global__ void __launch_bounds__(512) fused_outer_sharded_kernel(
+    float* __restrict__ theta_outer, float* __restrict__ buf, float* theta_local, __nv_bfloat16* __restrict__ shadow,
+    float* theta_mc, PeerPtrs flag_ptrs, int rank, int world, long long n, float lr, float mu, int nesterov, unsigned seq,
+    unsigned launch_idx, int nchunk, int n_comm, PipeCounters* cnt, int* timeout_flag, long long* fingerprint) {
+  const long long n4 = n / 4;                       // float4 vectors
+  const long long slab4 = n4 / world;               // per owner
+  const long long sub4 = slab4 / nchunk;            // per (owner, chunk)
+  const float inv_world = 1.f / (float)world;
+  unsigned* my_flags = reinterpret_cast<unsigned*>(flag_ptrs.p[rank]);
+  const int DONE_OFF = kMaxChunks * kMaxPeers;
+  __shared__ int s_last;
+  __shared__ long long s_fp[16];
+
+  if ((int)blockIdx.x < n_comm) {
+    // ------------------------------------------------------------------------------- owner CTAs: reduce, update, multicast
+    if (threadIdx.x < world)
+      st_release_sys(reinterpret_cast<unsigned*>(flag_ptrs.p[threadIdx.x]) + rank, seq);       // ready[0][rank] on every peer
+    if (!wait_flags(my_flags, world, seq, timeout_flag)) return;
+    const long long ctid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long cthreads = (long long)n_comm * blockDim.x;
+    for (int c = 0; c < nchunk; ++c) {
+      const long long lo = (long long)rank * slab4 + (long long)c * sub4, hi = lo + sub4;
+      constexpr int U = 4;
+      for (long long i0 = lo + ctid; i0 < hi; i0 += cthreads * U) {
+        float4 sv[U], to[U], bb[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const long long i = i0 + u * cthreads;
+          if (i < hi) {
+            sv[u] = multimem_ld_reduce_f32x4_weak(theta_mc + i * 4);
+            to[u] = ld_f4(theta_outer + i * 4);
+            bb[u] = ld_f4(buf + i * 4);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const long long i = i0 + u * cthreads;
+          if (i < hi) {
+            float* T = &to[u].x; float* B = &bb[u].x; const float* S = &sv[u].x;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float d = T[j] - S[j] * inv_world;
+              B[j] = mu * B[j] + d;
+              const float stp = nesterov ? (d + mu * B[j]) : B[j];
+              T[j] -= lr * stp;
+            }
+            st_f4(theta_outer + i * 4, to[u]);
+            st_f4(buf + i * 4, bb[u]);
+            multimem_st_f32x4_weak(theta_mc + i * 4, to[u]);
+          }
+        }
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) s_last = (atomicAdd(&cnt->done[c], 1u) + 1u == (unsigned)n_comm * launch_idx);
+      __syncthreads();
+      if (s_last && threadIdx.x < world) {
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned*>(flag_ptrs.p[threadIdx.x]) + DONE_OFF + c * kMaxPeers + rank, seq);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------------------- post CTAs: shadow + theta_outer refresh
+    const int n_local = gridDim.x - n_comm;
+    const long long ltid = (long long)(blockIdx.x - n_comm) * blockDim.x + threadIdx.x;
+    const long long lthreads = (long long)n_local * blockDim.x;
+    long long fp = 0;
+    for (int c = 0; c < nchunk; ++c) {
+      if (!wait_flags(my_flags + DONE_OFF + c * kMaxPeers, world, seq, timeout_flag)) return;
+      __threadfence_system();
+      for (int owner = 0; owner < world; ++owner) {
+        const long long lo = (long long)owner * slab4 + (long long)c * sub4, hi = lo + sub4;
+        for (long long i = lo + ltid; i < hi; i += lthreads) {
+          const float4 t = ld_vol_f4(theta_local + i * 4);           // written by the owner's multicast store
+          if (owner != rank) st_f4(theta_outer + i * 4, t);
+          if (shadow) *reinterpret_cast<uint2*>(shadow + i * 4) = make_uint2(f2_to_bf2(t.x, t.y), f2_to_bf2(t.z, t.w));
+          fp += (long long)__float_as_int(t.x) + (long long)__float_as_int(t.y) + (long long)__float_as_int(t.z) +
+                (long long)__float_as_int(t.w);
+        }
+      }
+    }
+    if (fingerprint) {      // wrap-around integer checksum of the new theta (order independent): the drift detector
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) fp += __shfl_xor_sync(0xffffffffu, fp, o);
+      if ((threadIdx.x & 31) == 0) s_fp[threadIdx.x >> 5] = fp;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        long long tot = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_fp[w];
+        atomicAdd(reinterpret_cast<unsigned long long*>(fingerprint), (unsigned long long)tot);
+      }
+    }
+  }
+}
+
+// theta_local / theta_mc: this rank's window of the symmetric master-weight allocation and its multicast alias, both
+// already offset to the slice the outer group averages.  n % (4 * world * nchunk) must be 0.  `fingerprint` (int64, may be
+// null) must be zeroed by the caller.
+ODB_EXPORT int odb_fused_outer_sharded(void* theta_outer, void* buf, void* theta_local, void* shadow, void* theta_mc,
+                                       const void* const* flag_ptrs, int rank, int world, long long n, float lr, float mu,
+                                       int nesterov, unsigned seq, unsigned launch_idx, int nchunk, int n_comm, void* cnt,
+                                       void* timeout_flag, void* fingerprint, cudaStream_t st) {
+  if (world > kMaxPeers || nchunk > kMaxChunks || nchunk < 1 || theta_mc == nullptr) return -1;
+  if (n % (4ll * world * nchunk)) return -2;
+  PeerPtrs fp{};
+  for (int i = 0; i < world; ++i) fp.p[i] = const_cast<void*>(flag_ptrs[i]);
+  void* fn = (void*)fused_outer_sharded_kernel<0>;
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 512, 0);
+  if (e != cudaSuccess) return (int)e;
+  if (per_sm < 1) return -3;
+  const int grid = sm_count() * (per_sm > 2 ? 2 : per_sm);
+  if (n_comm <= 0 || n_comm >= grid) n_comm = grid / 2;
+  float* a0 = (float*)theta_outer; float* a1 = (float*)buf; float* a2 = (float*)theta_local;
+  __nv_bfloat16* a3 = (__nv_bfloat16*)shadow; float* a4 = (float*)theta_mc; int* tf = (int*)timeout_flag;
+  PipeCounters* pc = (PipeCounters*)cnt; long long* fpr = (long long*)fingerprint;
+  void* args[] = {&a0, &a1, &a2, &a3, &a4, &fp, &rank, &world, &n, &lr, &mu, &nesterov, &seq, &launch_idx, &nchunk, &n_comm,
+                  &pc, &tf, &fpr};
+  e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(512), args, 0, st);   // cooperative = all CTAs co-resident (they spin)
+  return (int)e;
+}
+
+ODB_EXPORT int odb_outer_set_timeout_ms(int ms) {
+  const unsigned long long ns = (unsigned long long)(ms > 0 ? ms : 1) * 1000000ull;
+  return (int)cudaMemcpyToSymbol(g_outer_timeout_ns, &ns, sizeof(ns));
 }
 
 // Pipelined launch (multimem only).  `cnt` = zero-initialised PipeCounters in device memory owned by the caller;

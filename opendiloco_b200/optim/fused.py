@@ -58,6 +58,20 @@ class FlatView:
         return buf[self.offsets[i]:self.offsets[i] + p.numel()].view(p.shape)
 
     @torch.no_grad()
+    def rehome(self, new_flat: torch.Tensor) -> None:
+        """Move the fp32 master weights into ``new_flat`` (e.g. an NVLink symmetric-memory allocation) and re-point every
+        parameter view at it.  Values are preserved; optimizer moments / gradients are separate buffers and stay."""
+        assert new_flat.numel() == self.flat.numel() and new_flat.dtype == self.flat.dtype and new_flat.device == self.flat.device
+        new_flat.copy_(self.flat)
+        fp32_compute = self.shadow is None
+        if self.arena is not None:
+            self.arena.adopt_master(new_flat)
+        self.flat = new_flat
+        for p, o in zip(self.params, self.offsets):
+            p.data = new_flat[o:o + p.numel()].view(p.shape)
+        assert fp32_compute == (self.shadow is None)
+
+    @torch.no_grad()
     def gather_compute_weights(self) -> None:
         """After a sharded update: every rank publishes its slice of the compute weights (bf16 shadow, or fp32 master
         when computing in fp32) to the worker's other GPUs."""

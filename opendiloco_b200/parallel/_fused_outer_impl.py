@@ -21,6 +21,10 @@ _lib.register_optional("odb_fused_outer_step", [c_void_p, c_void_p, c_void_p, c_
 _lib.register_optional("odb_fused_outer_pipelined", [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                                     c_ll, c_float, c_float, c_int, c_uint, c_uint, c_int, c_int, c_int, c_void_p,
                                                     c_void_p, c_void_p])
+_lib.register_optional("odb_fused_outer_sharded", [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll,
+                                                  c_float, c_float, c_int, c_uint, c_uint, c_int, c_int, c_void_p, c_void_p,
+                                                  c_void_p, c_void_p])
+_lib.register_optional("odb_outer_set_timeout_ms", [c_int])
 logger = get_logger()
 MAX_CHUNKS, MAX_PEERS = 64, 16
 FLAG_WORDS = 2 * MAX_CHUNKS * MAX_PEERS     # pipelined kernel: ready[chunk][peer] | done[chunk][peer]; phase-sequential kernel uses the first 32
@@ -68,11 +72,60 @@ class FusedOuterStep:
             self.nchunk //= 2
         self.pipelined = bool(self.mc_ptr) and self.nchunk >= 2 and os.environ.get("ODB_OUTER_PIPELINED", "1") != "0" \
             and _lib.has_symbol("odb_fused_outer_pipelined")
+        # bounded cross-GPU waits: a missing peer raises the flag after this long (the host then raises, see poll_timeout)
+        if _lib.has_symbol("odb_outer_set_timeout_ms"):
+            lib = _lib.cuda_lib()
+            lib.odb_outer_set_timeout_ms(int(float(os.environ.get("ODB_OUTER_TIMEOUT_S", 20.0)) * 1e3))
+        self._tf_host = torch.zeros(1, dtype=torch.int32, pin_memory=True)
+        self._tf_event: torch.cuda.Event | None = None
+        self.fingerprint: torch.Tensor | None = None
+        # ---- sharded in-place form (fp32 transport): the master weights themselves live in a symmetric window
+        self.sharded = False
+        self._side = None                 # side stream of the background momentum re-replication
+        self._regather_pending = False
+        want_sharded = (not delta_bf16 and bool(self.mc_ptr) and os.environ.get("ODB_OUTER_SHARDED", "1") != "0"
+                        and _lib.has_symbol("odb_fused_outer_sharded") and sa.theta_outer.dtype == torch.float32)
+        if want_sharded:
+            try:
+                self._init_sharded(symm_mem, gname)
+            except Exception as e:        # keep the replicated-update kernel
+                logger.warning(f"sharded outer step unavailable ({type(e).__name__}: {e}); using the replicated-update kernel")
+                self.sharded = False
         torch.cuda.synchronize(dev)
         self.h_flag.barrier()
+        mode = "sharded in-place x" + str(self.nchunk_sh) if self.sharded else \
+            ("pipelined x" + str(self.nchunk) if self.pipelined else "phase-sequential")
         logger.info(f"fused outer step: {self.world} ranks, window {self.n * self.window.element_size() / 1e6:.0f} MB "
-                    f"{'bf16' if delta_bf16 else 'fp32'}, multimem={'yes' if self.mc_ptr else 'no (P2P loads/stores)'}, "
-                    f"{'pipelined x' + str(self.nchunk) if self.pipelined else 'phase-sequential'}")
+                    f"{'bf16' if delta_bf16 else 'fp32'}, multimem={'yes' if self.mc_ptr else 'no (P2P loads/stores)'}, {mode}")
+
+    def _init_sharded(self, symm_mem, gname: str) -> None:
+        """Re-home the fp32 master weights into a symmetric allocation (so the switch can reduce / multicast them in
+        place) and set up the sharded kernel's bookkeeping."""
+        sa, fv = self.sa, self.sa.fv
+        dev = sa.theta_outer.device
+        nch = int(os.environ.get("ODB_OUTER_CHUNKS", 16))
+        while nch > 1 and self.n % (4 * self.world * nch):
+            nch //= 2
+        if self.n % (4 * self.world * nch):
+            raise ValueError("parameter vector not divisible into slabs")
+        master = symm_mem.empty(fv.flat.numel(), dtype=torch.float32, device=dev)
+        h = symm_mem.rendezvous(master, gname)
+        mc = int(getattr(h, "multicast_ptr", 0) or 0)
+        if not mc:
+            raise RuntimeError("no multicast address for the master-weight window")
+        fv.rehome(master)
+        self.master, self.h_master = master, h
+        lo = fv.lo
+        sa.theta_local = fv.own(fv.flat)
+        self.opt.diloco_grad_averager._flat = (sa.theta_outer, sa.delta, sa.theta_local)
+        self._theta_mc = mc + lo * 4
+        self.nchunk_sh = nch
+        self.counters_sh = torch.zeros(2 * MAX_CHUNKS, dtype=torch.int32, device=dev)
+        self.launch_idx_sh = 0
+        self.fingerprint = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.slab = self.n // self.world
+        self._side = torch.cuda.Stream(device=dev)
+        self.sharded = True
 
     @classmethod
     def try_create(cls, opt, compression=None):
@@ -97,6 +150,24 @@ class FusedOuterStep:
         sa = self.sa
         g = sa._sgd_hparams()
         lib = _lib.cuda_lib()
+        if self.sharded:
+            self.wait_momentum()            # the previous background all-gather reads the slab this launch rewrites
+            self.launch_idx_sh += 1
+            self.fingerprint.zero_()
+            rc = lib.odb_fused_outer_sharded(
+                sa.theta_outer.data_ptr(), sa.momentum_buffer.data_ptr(), sa.theta_local.data_ptr(),
+                sa.shadow_local.data_ptr() if sa.shadow_local is not None else None, self._theta_mc, self._flag_ptrs,
+                self.rank, self.world, self.n, float(g["lr"]), float(g["momentum"]), int(bool(g.get("nesterov", False))),
+                self.seq, self.launch_idx_sh, self.nchunk_sh, int(os.environ.get("ODB_OUTER_COMM_CTAS", 0)),
+                self.counters_sh.data_ptr(), self.timeout_flag.data_ptr(), self.fingerprint.data_ptr(),
+                _lib.stream_ptr(sa.theta_outer))
+            _lib.check(rc, "fused_outer_sharded")
+            _lib.count_launch()
+            self.seq += 2
+            self._arm_timeout_probe()
+            self._regather_pending = True
+            sa.fv.gather_compute_weights()
+            return
         if self.pipelined:
             self.launch_idx += 1
             rc = lib.odb_fused_outer_pipelined(
@@ -109,6 +180,7 @@ class FusedOuterStep:
             _lib.check(rc, "fused_outer_pipelined")
             _lib.count_launch()
             self.seq += 2
+            self._arm_timeout_probe()
             sa.fv.gather_compute_weights()
             return
         rc = lib.odb_fused_outer_step(
@@ -121,7 +193,51 @@ class FusedOuterStep:
         _lib.check(rc, "fused_outer_step")
         _lib.count_launch()
         self.seq += 2
+        self._arm_timeout_probe()
         sa.fv.gather_compute_weights()
+
+    # ------------------------------------------------------------------ background re-replication of the momentum
+    def start_momentum_regather(self) -> None:
+        """Sharded form only: every owner publishes its momentum slab to the peers with ONE all-gather on a side stream,
+        overlapped with the next inner steps (the critical path of the outer step never touches foreign momentum)."""
+        if not (self.sharded and self._regather_pending):
+            return
+        self._regather_pending = False
+        buf = self.sa.momentum_buffer
+        cur = torch.cuda.current_stream(buf.device)
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            dist.all_gather_into_tensor(buf, buf[self.rank * self.slab:(self.rank + 1) * self.slab], group=self.group)
+
+    def wait_momentum(self) -> None:
+        """Make the current stream see the fully replicated momentum (no-op unless a re-gather is in flight)."""
+        if self._side is not None:
+            if self._regather_pending:
+                self.start_momentum_regather()
+            torch.cuda.current_stream(self.sa.momentum_buffer.device).wait_stream(self._side)
+
+    # ------------------------------------------------------------------ time-out reporting
+    def _arm_timeout_probe(self) -> None:
+        self._tf_host.copy_(self.timeout_flag, non_blocking=True)
+        if self._tf_event is None:
+            self._tf_event = torch.cuda.Event()
+        self._tf_event.record()
+
+    def poll_timeout(self, block: bool = False) -> None:
+        """Raise if the last fused round gave up waiting for a peer (the kernel then left theta / momentum untouched, but
+        the swarm is out of step: the caller must not train on).  Non-blocking unless ``block``."""
+        ev = self._tf_event
+        if ev is None:
+            return
+        if block:
+            ev.synchronize()
+        elif not ev.query():
+            return
+        self._tf_event = None
+        if int(self._tf_host[0]) != 0:
+            raise RuntimeError("fused outer step: a peer did not reach the NVLink barrier within ODB_OUTER_TIMEOUT_S "
+                               "(worker lost?); the outer update was NOT applied - restart from the last checkpoint or "
+                               "run with --hv.fused-collective false")
 
     def phase_times_us(self) -> dict | None:
         if self.stamps is None:

@@ -360,7 +360,7 @@ class DiLoCoStateAverager:
     def __init__(self, *, params, optimizer: Callable, inner_optimizer: torch.optim.Optimizer, num_inner_steps: int,
                  scheduler: Callable | None = None, dht: DHT | None = None, prefix: str = "diloco_state_averager",
                  offload_device: str | torch.device | None = None, flat_view: FlatView | None = None,
-                 average_state_every: int = 0, **_ignored):
+                 average_state_every: int = 1, **_ignored):
         self.dht, self.prefix = dht, prefix
         self.inner_optimizer, self.num_inner_steps = inner_optimizer, num_inner_steps
         self.main_parameters = list(params)
@@ -511,7 +511,7 @@ class DiLoCoOptimizer:
                  scheduler: Callable | None = None, averager_opts: dict | None = None, grad_compression=None,
                  tracker_opts: dict | None = None, all_reduce_strategy: AllReduceStrategy = AllReduceStrategy.WAIT_FOR_ALL,
                  timeout_waiting_for_peers: float | None = None, matchmaking_time: float | None = 15.0,
-                 averaging_timeout: float | None = 60.0, average_state_every: int = 0, verbose: bool = False,
+                 averaging_timeout: float | None = 60.0, average_state_every: int = 1, verbose: bool = False,
                  offload_device=None, fused_collective: bool | None = None, **kwargs):
         self._check_kwargs(kwargs)
         all_reduce_strategy = AllReduceStrategy(all_reduce_strategy) if not isinstance(all_reduce_strategy, AllReduceStrategy) \
@@ -567,6 +567,9 @@ class DiLoCoOptimizer:
                                              publish=(all_reduce_strategy == AllReduceStrategy.NO_WAIT
                                                       or getattr(dht, "board", None) is not None), **topts)
         self._schema_hash = self._compute_schema_hash()
+        self._drifted = False
+        self._fp_pending = None          # (event, pinned [max, -min] fingerprint of theta_outer after the last full round)
+        self._ns = self._make_namespace()
         self._fused = None
         want_fused = fused_collective if fused_collective is not None else True
         if want_fused and self.num_peers > 1 and sa.theta_outer.is_cuda and (grad_compression is None or grad_compression.is_identity
@@ -603,6 +606,56 @@ class DiLoCoOptimizer:
         if kwargs:
             raise TypeError(f"unexpected arguments for DiLoCoOptimizer: {sorted(kwargs)}")
 
+    def _make_namespace(self) -> str:
+        """"<incarnation nonce>/g<first global rank of the outer group>": agreed on collectively at construction."""
+        group = self.dht.group if self.dht is not None else None
+        if comm.group_size(group) <= 1:
+            return "solo"
+        dev = comm_device(group, torch.device("cpu"))
+        nonce = torch.tensor([time.time_ns() & ((1 << 62) - 1)], dtype=torch.int64, device=dev)
+        comm.broadcast_(nonce, 0, group)
+        first = dist.get_process_group_ranks(group)[0] if group is not dist.group.WORLD else 0
+        return f"{int(nonce.item()):x}/g{first}"
+
+    # ------------------------------------------------------------------------------------------ state fingerprints
+    def _post_state_fingerprint(self) -> None:
+        """After a full round: wrap-around integer checksum of theta_outer (+ momentum), all-reduced to (max, -min) over
+        the swarm and copied to pinned memory WITHOUT a host sync; looked at when the next round starts."""
+        sa = self.state_averager
+        group = self.dht.group if self.dht is not None else None
+        if comm.group_size(group) <= 1 or sa.theta_outer.dtype != torch.float32:
+            return
+        if self._fused is not None and self._fused.fingerprint is not None:
+            fp = self._fused.fingerprint.clone()                      # produced by the fused kernel's last pass
+        else:
+            fp = sa.theta_outer.view(torch.int32).sum(dtype=torch.int64)
+            if sa.momentum_buffer is not None:
+                fp = fp + 3 * sa.momentum_buffer.view(torch.int32).sum(dtype=torch.int64)
+        pair = torch.stack([fp.reshape(()), -fp.reshape(())]).to(comm_device(group, fp.device))
+        dist.all_reduce(pair, op=dist.ReduceOp.MAX, group=group)          # [max fp, -min fp]
+        if pair.is_cuda:
+            host = torch.empty(2, dtype=torch.int64, pin_memory=True)
+            host.copy_(pair, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._fp_pending = (ev, host)
+        else:
+            self._fp_pending = (None, pair.clone())
+
+    def _state_diverged(self) -> bool:
+        """Did the workers hold different theta_outer / momentum after the previous full round?  (Same answer on every
+        worker: it is computed from an all-reduced value.)"""
+        if self._fp_pending is None:
+            return False
+        ev, host = self._fp_pending
+        self._fp_pending = None
+        if ev is not None:
+            ev.synchronize()             # recorded a whole epoch ago
+        diverged = int(host[0]) != -int(host[1])
+        if diverged:
+            logger.warning("theta_outer / outer momentum differ between workers: running a state-averaging round")
+        return diverged
+
     def _compute_schema_hash(self) -> int:
         return hash(tuple(tuple(p.shape) for p in self.state_averager.offloaded_parameters))
 
@@ -635,6 +688,8 @@ class DiLoCoOptimizer:
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        if self._fused is not None:
+            self._fused.poll_timeout(block=False)        # did the last fused outer round give up on a peer?
         if self._should_load_state_from_peers():
             logger.log(self.status_loglevel, "Peer is out of sync")
             if self.all_reduce_strategy == AllReduceStrategy.NO_WAIT:
@@ -646,7 +701,10 @@ class DiLoCoOptimizer:
         self.tracker.report_local_progress(self.local_epoch, self.tracker.local_progress.samples_accumulated + batch_size)
         self._maybe_schedule_gradient_averaging()
         if scaler is not None:
-            scaler.step(self.inner_optimizer)
+            if _is_fused(self.inner_optimizer):
+                self.inner_optimizer.step_scaled(scaler)      # unscale + inf check + clip + AdamW in the fused kernels
+            else:
+                scaler.step(self.inner_optimizer)
             from ..utils.training import found_inf_grad
 
             if found_inf_grad(self.inner_optimizer, scaler):
@@ -675,94 +733,97 @@ class DiLoCoOptimizer:
             if c is None or c.triggered or c.done():
                 self.scheduled_diloco_grads = self.diloco_grad_averager.schedule_step(timeout=self.averaging_timeout)
 
-    def _wait_for_peers(self) -> list[int] | None:
-        """Arrival handshake through the rendezvous store.  Returns the ranks (in the outer group) that take part in
-        this round, or None for "everyone".  WAIT_FOR_ALL waits up to ``timeout_waiting_for_peers`` for the slowest
-        worker (hivemind_diloco.py:578-608); NO_WAIT gives late workers ``matchmaking_time`` seconds."""
-        store = self.dht.store() if self.dht is not None else None
-        n = self.num_peers
-        if store is None or n <= 1:
-            return None
-        if self.all_reduce_strategy == AllReduceStrategy.WAIT_FOR_ALL and self.timeout_waiting_for_peers is None:
-            return None
-        epoch, me = self.local_epoch, self.dht.rank_in_group
-        key = lambda r: f"{self.run_id}/arrive/{epoch}/{r}"  # noqa: E731
-        inject = os.environ.get("ODB_FAULT_INJECT")      # "rank:epoch[:seconds]" - that worker arrives late (or never)
-        if inject:
-            f = inject.split(":")
-            if int(f[0]) == me and int(f[1]) == epoch:
-                delay = float(f[2]) if len(f) > 2 else 1e9
-                logger.warning(f"fault injection: worker {me} stalls {delay:.1f}s before outer step {epoch}")
-                time.sleep(min(delay, 3600.0))
-        store.set(key(me), "1")
-        budget = self.timeout_waiting_for_peers if self.all_reduce_strategy == AllReduceStrategy.WAIT_FOR_ALL \
-            else self.matchmaking_time
-        deadline = time.perf_counter() + float(budget)
-        keys = [key(r) for r in range(n)]
-        t_start = time.perf_counter()
-        while time.perf_counter() < deadline:
-            try:
-                if store.check(keys):
-                    return None
-            except Exception:
-                return None
-            # workers of a healthy swarm arrive within microseconds of each other: spin first, back off later
-            if time.perf_counter() - t_start > 0.002:
-                time.sleep(0.0005)
-        present = [r for r in range(n) if store.check([key(r)])]
-        logger.log(self.status_loglevel, f"Timeout waiting for peers, going to skip slowest peers; present={present}")
-        return present
+    # ------------------------------------------------------------------------------------------ round formation
+    def _key(self, *parts) -> str:
+        """Board key of this swarm INCARNATION and this outer group.  The nonce (agreed on at construction) keeps a
+        restarted job from replaying the round records of its previous life on a long-lived board; the group tag keeps the
+        outer groups of a multi-GPU worker (one per local rank) from sharing counters and member lists."""
+        return "/".join([self.run_id, self._ns, *map(str, parts)])
 
-    # ------------------------------------------------------------------------------------------ elastic rounds (NO_WAIT)
-    def _form_round(self) -> tuple[list[int], bool] | None:
-        """NO_WAIT matchmaking through the membership board (hivemind: the fastest peer triggers the round and whoever
-        shows up within ``matchmaking_time`` joins it; the others form the next round among themselves).  The first
-        arrival of round r of this epoch is its leader: it waits ``matchmaking_time`` (or until nobody else can come),
-        publishes the member list and everybody listed averages with point-to-point transfers - ranks that are still
-        training are not needed.  Returns (sorted member ranks, am_i_leader), or None when there is no board."""
+    def _inject_fault(self, epoch: int, me: int) -> None:
+        inject = os.environ.get("ODB_FAULT_INJECT")      # "rank:epoch[:seconds]" - that worker arrives late (or never)
+        if not inject:
+            return
+        f = inject.split(":")
+        if int(f[0]) == me and int(f[1]) == epoch:
+            delay = float(f[2]) if len(f) > 2 else 1e9
+            logger.warning(f"fault injection: worker {me} stalls {delay:.1f}s before outer step {epoch}")
+            time.sleep(min(delay, 3600.0))
+
+    def _form_round(self) -> tuple[list[int], bool, bool] | None:
+        """Matchmaking through the membership board, for both strategies (hivemind: the round is formed by whoever shows
+        up inside the window; the others form the next round among themselves).  The first arrival of round r of this
+        epoch is its leader: it waits until everybody still missing has arrived or the window closes -
+        ``timeout_waiting_for_peers`` for WAIT_FOR_ALL ("Timeout waiting for peers, going to skip slowest peers",
+        hivemind_diloco.py:584-607), ``matchmaking_time`` for NO_WAIT - then publishes the member list.  A partial round
+        averages over the members only (point-to-point or a member-masked NVLink window), so workers that are still
+        training - or dead - are not needed.
+        Returns (sorted member ranks, am_i_leader, repair) or None when there is no board.  ``repair``: some member saw a
+        split epoch or adopted the swarm state since the last full round -> this full round also averages the state.
+        Store errors propagate: a broken board must not be mistaken for "everyone arrived"."""
         store = self.dht.store() if self.dht is not None else None
         n = self.num_peers
         if store is None or n <= 1:
             return None
         epoch, me = self.local_epoch, self.dht.rank_in_group
-        inject = os.environ.get("ODB_FAULT_INJECT")      # "rank:epoch[:seconds]" - that worker arrives late
-        if inject:
-            f = inject.split(":")
-            if int(f[0]) == me and int(f[1]) == epoch:
-                delay = float(f[2]) if len(f) > 2 else 1e9
-                logger.warning(f"fault injection: worker {me} stalls {delay:.1f}s before outer step {epoch}")
-                time.sleep(min(delay, 3600.0))
-        base = f"{self.run_id}/round/{epoch}"
+        self._inject_fault(epoch, me)
+        window = float(self.timeout_waiting_for_peers if self.all_reduce_strategy == AllReduceStrategy.WAIT_FOR_ALL
+                       else self.matchmaking_time)
         done_before = 0                                  # peers that already finished this epoch in earlier rounds
         r = 0
+        mark = "D" if self._drifted else "1"
         while True:
-            mkey = f"{base}/{r}/members"
+            mkey = self._key("round", epoch, r, "members")
             if store.check([mkey]):                      # round r is closed: try the next one
-                done_before += len(store.get(mkey).decode().split(","))
+                done_before += len(store.get(mkey).decode().split("|")[0].split(","))
                 r += 1
                 continue
-            order = int(store.add(f"{base}/{r}/count", 1))
-            store.set(f"{base}/{r}/arrive/{me}", "1")
-            keys = [f"{base}/{r}/arrive/{q}" for q in range(n)]
+            order = int(store.add(self._key("round", epoch, r, "count"), 1))
+            store.set(self._key("round", epoch, r, "arrive", me), mark)
+            keys = [self._key("round", epoch, r, "arrive", q) for q in range(n)]
+            t_start = time.perf_counter()
             if order == 1:
-                deadline = time.perf_counter() + float(self.matchmaking_time)
+                deadline = t_start + window
                 while time.perf_counter() < deadline:
                     if sum(store.check([k]) for k in keys) >= n - done_before:
                         break
-                    time.sleep(0.001)
+                    # workers of a healthy swarm arrive within microseconds of each other: spin first, back off later
+                    if time.perf_counter() - t_start > 0.002:
+                        time.sleep(0.0005)
                 members = [q for q in range(n) if store.check([keys[q]])]
-                store.set(mkey, ",".join(str(q) for q in members))
-                return members, True
-            deadline = time.perf_counter() + float(self.matchmaking_time) + float(self.averaging_timeout or 60.0)
+                repair = any(store.get(keys[q]).decode() == "D" for q in members)
+                store.set(mkey, ",".join(str(q) for q in members) + "|" + ("1" if repair else "0"))
+                if len(members) < n - done_before:
+                    logger.log(self.status_loglevel, f"Timeout waiting for peers, going to skip slowest peers; present={members}")
+                self._gc_round_keys(store, epoch - 2, n)
+                return members, True, repair
+            deadline = t_start + window + float(self.averaging_timeout or 60.0)
             while not store.check([mkey]):
                 if time.perf_counter() > deadline:
                     raise TimeoutError(f"round {r} of outer step {epoch}: the leader never published the member list")
-                time.sleep(0.001)
-            members = [int(q) for q in store.get(mkey).decode().split(",")]
+                if time.perf_counter() - t_start > 0.002:
+                    time.sleep(0.0005)
+            rec = store.get(mkey).decode().split("|")
+            members = [int(q) for q in rec[0].split(",")]
             if me in members:
-                return members, False
+                return members, False, rec[1] == "1"
             done_before += len(members)                  # my arrival raced with the leader's snapshot: next round
             r += 1
+
+    def _gc_round_keys(self, store, epoch: int, n: int) -> None:
+        """Drop the records of a long-closed epoch (best effort: c10d TCPStore and the native board can delete)."""
+        if epoch < 0 or not hasattr(store, "delete_key"):
+            return
+        try:
+            for r in range(n):
+                if not store.check([self._key("round", epoch, r, "count")]):
+                    break
+                for k in ("members", "count"):
+                    store.delete_key(self._key("round", epoch, r, k))
+                for q in range(n):
+                    store.delete_key(self._key("round", epoch, r, "arrive", q))
+        except Exception:
+            pass
 
     def _serve_resync_requests(self) -> None:
         """Round leader, after its outer update: hand theta_outer / momentum / epoch to peers that fell behind and asked
@@ -772,15 +833,16 @@ class DiLoCoOptimizer:
         if store is None:
             return
         sa, me = self.state_averager, self.dht.rank_in_group
+        self._sync_outer_state()
         for q in range(self.num_peers):
-            rkey = f"{self.run_id}/resync/request/{q}"
+            rkey = self._key("resync", "request", q)
             if q == me or not store.check([rkey]):
                 continue
             req = store.get(rkey).decode()
-            if req == "" or int(store.add(f"{self.run_id}/resync/claim/{q}/{req}", 1)) != 1:
+            if req == "" or int(store.add(self._key("resync", "claim", q, req), 1)) != 1:
                 continue                                 # nothing pending, or another leader serves it
             logger.log(self.status_loglevel, f"serving swarm state (epoch {self.local_epoch}) to worker {q}")
-            store.set(f"{self.run_id}/resync/grant/{q}/{req}", f"{me},{self.local_epoch}")
+            store.set(self._key("resync", "grant", q, req), f"{me},{self.local_epoch}")
             bufs = [sa.theta_outer] + ([sa.momentum_buffer] if sa.momentum_buffer is not None else [])
             comm.p2p_send_(bufs, q, self.dht.group)
 
@@ -792,17 +854,17 @@ class DiLoCoOptimizer:
         sa, me = self.state_averager, self.dht.rank_in_group
         self._resync_seq = getattr(self, "_resync_seq", 0) + 1
         req = str(self._resync_seq)
-        store.set(f"{self.run_id}/resync/request/{me}", req)
-        gkey = f"{self.run_id}/resync/grant/{me}/{req}"
+        store.set(self._key("resync", "request", me), req)
+        gkey = self._key("resync", "grant", me, req)
         deadline = time.perf_counter() + float(self.averaging_timeout or 600.0)
         while not store.check([gkey]):
             if time.perf_counter() > deadline:
-                store.set(f"{self.run_id}/resync/request/{me}", "")
+                store.set(self._key("resync", "request", me), "")
                 logger.warning("no round leader served the state request in time; continuing with the local state")
                 return False
             time.sleep(0.005)
         src, epoch = (int(x) for x in store.get(gkey).decode().split(","))
-        store.set(f"{self.run_id}/resync/request/{me}", "")
+        store.set(self._key("resync", "request", me), "")
         with self.tracker.pause_updates():
             bufs = [sa.theta_outer] + ([sa.momentum_buffer] if sa.momentum_buffer is not None else [])
             comm.p2p_recv_(bufs, src, self.dht.group)
@@ -810,6 +872,9 @@ class DiLoCoOptimizer:
             sa.apply_optimizer_parameters()
             self.tracker.update_epoch(epoch)
             self.tracker.report_local_progress(epoch, samples_accumulated=0)
+        # the state came from ONE peer of a swarm that split: have the next full round average it (the flag travels with
+        # this worker's arrival record, so every member of that round takes the same decision)
+        self._drifted = True
         logger.log(self.status_loglevel, f"adopted the swarm state of worker {src} at epoch {epoch}")
         return True
 
@@ -818,34 +883,36 @@ class DiLoCoOptimizer:
         assert self._schema_hash == self._compute_schema_hash(), "parameters changed during iteration"
         t_start = time.perf_counter()
         sa, ga = self.state_averager, self.diloco_grad_averager
-        members, leader = None, False
-        if self.num_peers > 1 and self.all_reduce_strategy == AllReduceStrategy.NO_WAIT:
+        members, leader, repair = None, False, False
+        if self._fused is not None:
+            self._fused.poll_timeout(block=True)         # the previous fused round must have completed on every rank
+        if self.num_peers > 1:
             formed = self._form_round()
             if formed is not None:
-                members, leader = formed
+                members, leader, repair = formed
                 if len(members) == self.num_peers:
                     members = None                       # everybody made it: the ordinary full-group round
                 else:
                     logger.log(self.status_loglevel, f"outer step {self.local_epoch}: elastic round with workers {members} "
                                                      f"of {self.num_peers}")
-        elif self.num_peers > 1:
-            present = self._wait_for_peers()
-            if present is not None and len(present) < self.num_peers:
-                raise RuntimeError(
-                    f"DiLoCo worker(s) missing at outer step {self.local_epoch}: present ranks {present} of {self.num_peers}. "
-                    "WAIT_FOR_ALL rounds need every worker; restart from the last checkpoint (--hv.fail_rank_drop "
-                    "semantics, train_fsdp.py:452-457) or use AllReduceStrategy.NO_WAIT for elastic rounds.")
         self.last_round_members = members if members is not None else list(range(self.num_peers))
         with self.tracker.pause_updates():
             next_epoch = max(self.local_epoch + 1, self.tracker.global_epoch) if members is None else self.local_epoch + 1
-            average_state = (self.num_peers > 1 and self.average_state_every > 0
-                             and next_epoch % self.average_state_every == 0)
+            # State averaging (hivemind average_state_every, default 1 = every epoch; hivemind_diloco.py:630-637).  After a
+            # full round every worker holds bit-identical theta_outer / momentum, so averaging them is the identity: the
+            # round is therefore run when it can change something - the swarm split since the last full round
+            # (``repair``, decided by the round leader from the members' arrival records, hence the same on every
+            # member), the fingerprints of the previous round disagreed (``_state_diverged``), or unconditionally with
+            # ODB_FORCE_STATE_AVERAGING=1.
+            due = self.num_peers > 1 and self.average_state_every > 0 and next_epoch % self.average_state_every == 0
+            average_state = due and members is None and (self._state_diverged() or os.environ.get("ODB_FORCE_STATE_AVERAGING") == "1")
             if members is not None:
                 self._drifted = True                     # the swarm split this epoch: theta_outer differs between rounds
-            elif getattr(self, "_drifted", False) and self.num_peers > 1:
-                # first full round after a split epoch (every worker saw the split): repair the drift by averaging
-                # theta_outer / momentum over everybody, what hivemind's state averaging does every epoch
-                average_state, self._drifted = True, False
+            elif self.num_peers > 1:
+                average_state = average_state or repair
+                self._drifted = False
+            if members is not None or average_state:
+                self._sync_outer_state()                 # these paths read / average the FULL outer momentum
             if members is not None and len(members) == 1:
                 # nobody else showed up in time: this worker's own pseudo-gradient is the round
                 sa.step(increment_epoch=True, optimizer_step=True, averaging_round=False, fused_solo=True)
@@ -857,6 +924,7 @@ class DiLoCoOptimizer:
             elif self._fused is not None:
                 self._fused.outer_step()                    # pseudo-grad + NVLink reduce + Nesterov in ONE kernel
                 sa.step(increment_epoch=True, optimizer_step=False, averaging_round=average_state)
+                self._fused.poll_timeout(block=False)
             elif self.num_peers > 1:
                 logger.log(self.status_loglevel, f"Beginning optimizer step #{self.local_epoch}")
                 ga.step(wait=True, timeout=self.averaging_timeout, control=self.scheduled_diloco_grads)
@@ -866,6 +934,10 @@ class DiLoCoOptimizer:
                 sa.step(increment_epoch=True, optimizer_step=True, averaging_round=average_state)
             else:
                 sa.step(increment_epoch=True, optimizer_step=True, averaging_round=False, fused_solo=True)
+            if self.num_peers > 1 and members is None and self.average_state_every > 0:
+                self._post_state_fingerprint()
+            if self._fused is not None:
+                self._fused.start_momentum_regather()    # background: owners publish their momentum slabs (side stream)
             if leader:
                 self._serve_resync_requests()
             if self.scheduled_state is not None and not self.scheduled_state.done():
@@ -875,6 +947,13 @@ class DiLoCoOptimizer:
             sa.state_sharing_priority = self.local_epoch
             logger.log(self.status_loglevel, f"Transitioning to epoch {self.local_epoch}")
         self.last_outer_step_seconds = time.perf_counter() - t_start
+
+    def _sync_outer_state(self) -> None:
+        """The sharded fused outer step keeps each momentum slab current on its owner only and re-replicates it in the
+        background; anything that reads the whole outer-optimizer state (checkpoints, partial rounds, state averaging,
+        serving a lagging peer) first waits for that all-gather."""
+        if self._fused is not None:
+            self._fused.wait_momentum()
 
     def update_main_param_after_outer_step(self) -> None:
         """No-op kept for API parity: the outer kernel already wrote theta_local (SURVEY.md §2.7 first quirk)."""
@@ -890,6 +969,7 @@ class DiLoCoOptimizer:
         if self.scheduled_diloco_grads is not None:
             self.scheduled_diloco_grads.cancel()
             self.scheduled_diloco_grads = None
+        self._sync_outer_state()
         with self.tracker.pause_updates():
             self.state_averager.load_state_from_peers()
             self.tracker.report_local_progress(self.local_epoch, samples_accumulated=0)
@@ -898,6 +978,7 @@ class DiLoCoOptimizer:
         """{"state_dict_outer": outer sd (+ ["state"]["local_epoch"]), "state_dict_inner": inner sd}
         (hivemind_diloco.py:697-707) plus what the reference forgets to save: theta_outer itself and the inner-step
         phase."""
+        self._sync_outer_state()
         sd_outer = self.state_averager.optimizer.state_dict()
         sd_outer["state"]["local_epoch"] = self.local_epoch
         return {
@@ -905,6 +986,7 @@ class DiLoCoOptimizer:
             "state_dict_inner": self.inner_optimizer.state_dict(),
             "theta_outer": self.state_averager.theta_outer.detach().cpu().clone(),
             "samples_accumulated": self.tracker.local_progress.samples_accumulated,
+            "drifted": bool(self._drifted),
         }
 
     def load_state_dict(self, state_dict: dict) -> None:
@@ -917,6 +999,7 @@ class DiLoCoOptimizer:
         self.inner_optimizer.load_state_dict(state_dict["state_dict_inner"])
         if state_dict.get("theta_outer") is not None:
             self.state_averager.theta_outer.copy_(state_dict["theta_outer"])
+        self._drifted = bool(state_dict.get("drifted", False))
         self.tracker.update_epoch(self.local_epoch)
         self.tracker.report_local_progress(self.local_epoch, int(state_dict.get("samples_accumulated", 0)))
 

@@ -206,7 +206,7 @@ def main(cfg: TorchDilocoConfig) -> None:
             h.remove()
         handles = []
         if scaler.is_enabled():
-            scaler.unscale_(inner)
+            inner.unscale_(scaler)
         model.clip_grad_norm_(1.0)
         norms = get_grad_norm(model) if log_act else None
         optimizer.step(scaler=scaler if scaler.is_enabled() else None)      # inner AdamW; outer step every local_steps

@@ -238,12 +238,13 @@ def train(config: Config) -> None:
         if is_accumulating:
             continue
 
-        scaler.unscale_(inner) if scaler.is_enabled() else None
+        if scaler.is_enabled():
+            inner.unscale_(scaler)        # 1/scale + inf check are folded into the fused norm / AdamW kernels (K11)
         model.clip_grad_norm_(1.0)
         if hv is not None:
             optimizer.step(scaler=scaler if scaler.is_enabled() else None)
         elif scaler.is_enabled():
-            scaler.step(optimizer)
+            optimizer.step_scaled(scaler)
         else:
             optimizer.step()
         scaler.update()

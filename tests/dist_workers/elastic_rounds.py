@@ -1,4 +1,4 @@
-"""Run under torchrun with 3 ranks (gloo on CPU).  AllReduceStrategy.NO_WAIT with a straggler: outer step 1 splits into
+"""Run under torchrun with 3 ranks (gloo on CPU, or NCCL on 3 GPUs with ODB_TEST_DEVICE=cuda).  AllReduceStrategy.NO_WAIT with a straggler: outer step 1 splits into
 the round of the two punctual workers and a solo round of the late one; outer step 2 is a full round again and repairs
 the drift with a state-averaging round.  Every transition is checked against values computed by hand."""
 import os
@@ -14,12 +14,14 @@ from opendiloco_b200.parallel import comm  # noqa: E402
 from opendiloco_b200.parallel.diloco import AllReduceStrategy, DiLoCoOptimizer  # noqa: E402
 from opendiloco_b200.parallel.swarm import DHT  # noqa: E402
 
-comm.init_distributed()
+cuda = os.environ.get("ODB_TEST_DEVICE", "cpu") == "cuda"
+comm.init_distributed("nccl" if cuda else "gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
+dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))) if cuda else torch.device("cpu")
 assert world == 3
 LATE, H = 2, 2
 os.environ["ODB_FAULT_INJECT"] = f"{LATE}:1:5.0"          # worker 2 reaches outer step 1 five seconds late
-p = torch.nn.Parameter(torch.zeros(64))
+p = torch.nn.Parameter(torch.zeros(64, device=dev))
 opt = DiLoCoOptimizer(dht=DHT(start=True), run_id="elastic", batch_size=1, num_inner_steps=H, params=[p],
                       outer_optimizer=partial(torch.optim.SGD, lr=1.0, momentum=0.0),
                       inner_optimizer=partial(torch.optim.SGD, lr=1.0), all_reduce_strategy=AllReduceStrategy.NO_WAIT,
@@ -35,12 +37,12 @@ def check(name, cond):
 
 # the subset butterfly itself: ranks 0 and 2 average a 1003-element vector (uneven slices), rank 1 is not involved
 if rank in (0, 2):
-    v = torch.arange(1003, dtype=torch.float32) * (rank + 1)
+    v = torch.arange(1003, dtype=torch.float32, device=dev) * (rank + 1)
     comm.p2p_all_reduce_mean_(v, [0, 2], dist.group.WORLD)
-    check("p2p subset mean", torch.allclose(v, torch.arange(1003, dtype=torch.float32) * 2.0))
-    w = torch.full((5,), float(rank), dtype=torch.bfloat16)          # fewer elements than members x 8: empty slices
+    check("p2p subset mean", torch.allclose(v, torch.arange(1003, dtype=torch.float32, device=dev) * 2.0))
+    w = torch.full((5,), float(rank), dtype=torch.bfloat16, device=dev)   # fewer elements than members x 8: empty slices
     comm.p2p_all_reduce_mean_(w, [0, 2], dist.group.WORLD)
-    check("p2p subset mean, tiny bf16", torch.allclose(w.float(), torch.full((5,), 1.0)))
+    check("p2p subset mean, tiny bf16", torch.allclose(w.float(), torch.full((5,), 1.0, device=dev)))
 
 
 def inner_steps(scale):
@@ -104,6 +106,17 @@ else:
     check("epoch after serving", opt.local_epoch == 8)
 dist.all_gather(gathered, p.data)
 check("laggard holds the swarm parameters", all(torch.equal(gathered[0], g) for g in gathered))
+
+# epoch 8: one more FULL round after the resync.  The laggard adopted the state of ONE peer, so it arrives flagged as
+# drifted; the round leader turns that into ``repair`` for every member - all three run the state-averaging collective
+# (a decision taken from process-local flags would leave the punctual workers out of it and dead-lock / corrupt the round)
+if rank != LATE:
+    time.sleep(1.0)
+inner_steps(rank + 1.0)
+check("epoch8 full round", opt.last_round_members == [0, 1, 2] and opt.local_epoch == 9)
+dist.all_gather(gathered, p.data)
+check("all workers agree after the post-resync round", all(torch.equal(gathered[0], g) for g in gathered))
+check("drift flag cleared", not opt._drifted)
 opt.shutdown()
 dist.barrier()
 print(f"[rank {rank}] {'ALL OK' if ok else 'SOME FAILED'}", flush=True)

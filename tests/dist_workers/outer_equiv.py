@@ -60,7 +60,9 @@ def oracle():
     return torch.cat([p.data.reshape(-1) for p in models[rank].parameters()])
 
 
-def ours(compression=None, fused=None):
+def ours(compression=None, fused=None, env=None):
+    for k, v in (env or {}).items():
+        os.environ[k] = v
     m = make_model()
     dht = DHT(start=True)
     opt = DiLoCoOptimizer(dht=dht, batch_size=16, num_inner_steps=H, params=m.parameters(),
@@ -75,31 +77,50 @@ def ours(compression=None, fused=None):
         opt.zero_grad()
     assert opt.local_epoch == STEPS // H
     used_fused = opt._fused is not None
+    mode = ("sharded" if opt._fused.sharded else "pipelined" if opt._fused.pipelined else "sequential") if used_fused else "-"
     out = torch.cat([p.data.reshape(-1) for p in m.parameters()])
+    # the FULL outer momentum must be identical on every worker (the sharded kernel re-replicates it in the background)
+    mom = opt.state_dict()["state_dict_outer"]["state"]
+    mom = torch.cat([mom[k]["momentum_buffer"].reshape(-1).to(dev) for k in sorted(k for k in mom if isinstance(mom[k], dict))])
+    # shadow (bf16 compute weights) must track the master weights after the outer step
+    fv = opt.inner_optimizer.fv
+    shadow_ok = fv.shadow is None or torch.equal(fv.shadow[:fv.flat.numel()].float(), fv.flat.to(fv.shadow.dtype).float())
     opt.shutdown()
-    return out, used_fused
+    for k in (env or {}):
+        os.environ.pop(k, None)
+    return out, used_fused, mode, mom, shadow_ok
 
 
 ref = oracle()
 results = {}
-cases = [("flat", None, False)]
+cases = [("flat", None, False, None)]
 if cuda:
-    cases += [("fused_fp32", None, True), ("fused_bf16", "bf16", True)]
-cases += [(c, c, False) for c in ("fp16", "bf16", "scaled-fp16", "uniform8bit", "quantile8bit", "blockwise8bit")]
-tol = {"flat": 2e-6, "fused_fp32": 2e-6, "fused_bf16": 2e-3, "fp16": 1e-3, "bf16": 3e-3, "scaled-fp16": 1e-3,
+    cases += [("fused_fp32", None, True, None),                                   # sharded in-place kernel when NVLS is there
+              ("fused_fp32_repl", None, True, {"ODB_OUTER_SHARDED": "0"}),        # replicated-update pipelined kernel
+              ("fused_fp32_seq", None, True, {"ODB_OUTER_SHARDED": "0", "ODB_OUTER_PIPELINED": "0"}),
+              ("fused_fp32_p2p", None, True, {"ODB_FUSED_OUTER_NO_MULTIMEM": "1"}),    # peer loads / stores, no multicast
+              ("fused_bf16", "bf16", True, None)]
+cases += [(c, c, False, None) for c in ("fp16", "bf16", "scaled-fp16", "uniform8bit", "quantile8bit", "blockwise8bit")]
+tol = {"flat": 2e-6, "fused_fp32": 2e-6, "fused_fp32_repl": 2e-6, "fused_fp32_seq": 2e-6, "fused_fp32_p2p": 2e-6,
+       "fused_bf16": 2e-3, "fp16": 1e-3, "bf16": 3e-3, "scaled-fp16": 1e-3,
        "uniform8bit": 8e-2, "quantile8bit": 8e-2, "blockwise8bit": 2e-2}
 ok = True
-for name, comp, fused in cases:
-    out, used = ours(comp, fused)
+for name, comp, fused, env in cases:
+    out, used, mode, mom, shadow_ok = ours(comp, fused, env)
     err = (out - ref).abs().max().item()
-    # all workers must hold identical parameters right after an outer step
+    # all workers must hold identical parameters (and outer momentum) right after an outer step
     gathered = [torch.empty_like(out) for _ in range(world)]
     dist.all_gather(gathered, out)
     spread = max((g - gathered[0]).abs().max().item() for g in gathered)
-    good = err < tol[name] and spread < 1e-6 and (not fused or used or os.environ.get("ODB_ALLOW_NO_FUSED"))
+    gm = [torch.empty_like(mom) for _ in range(world)]
+    dist.all_gather(gm, mom)
+    mspread = max((g - gm[0]).abs().max().item() for g in gm)
+    good = err < tol[name] and spread < 1e-6 and mspread < 1e-6 and shadow_ok and \
+        (not fused or used or os.environ.get("ODB_ALLOW_NO_FUSED"))
     ok &= good
     if rank == 0:
-        print(f"{name:14s} err={err:.3e} spread={spread:.1e} fused_used={used} {'OK' if good else 'FAIL'}", flush=True)
+        print(f"{name:16s} err={err:.3e} spread={spread:.1e} momentum_spread={mspread:.1e} shadow={'ok' if shadow_ok else 'BAD'} "
+              f"fused={mode} {'OK' if good else 'FAIL'}", flush=True)
 dist.barrier()
 comm.shutdown_distributed()
 sys.exit(0 if ok else 1)

@@ -244,3 +244,15 @@ def test_reference_import_paths_resolve():
         opt.step()
         opt.zero_grad()
     assert opt.local_epoch == 1 and set(opt.state_dict()) >= {"state_dict_outer", "state_dict_inner"}
+
+
+def test_wait_for_all_timeout_skips_the_slowest_peer_gloo():
+    """3 workers over gloo, WAIT_FOR_ALL + a straggler: after ``timeout_waiting_for_peers`` the round goes ahead with the
+    peers present (hivemind_diloco.py:584-607 "going to skip slowest peers") instead of raising; the straggler closes the
+    epoch alone and the next full round repairs the drift (tests/dist_workers/straggler_wait_for_all.py)."""
+    env = dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=3", "--master-addr", "127.0.0.1",
+           "--master-port", "29619", os.path.join(ROOT, "tests", "dist_workers", "straggler_wait_for_all.py")]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
+    assert "FAIL" not in res.stdout and res.stdout.count("ALL OK") == 3
