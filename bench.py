@@ -34,7 +34,9 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-fsdp"],
+                    help="ours | reference (unmodified train_diloco_torch.py, eager: the DiLoCo oracle) | reference-fsdp "
+                         "(unmodified train_fsdp.py, FSDP NO_SHARD + torch.compile: the stronger inner-step baseline)")
     ap.add_argument("--model", default="150m")
     ap.add_argument("--seq", type=int, default=1024)
     ap.add_argument("--batch", type=int, default=512, help="sequences per worker per optimizer step (reference --batch-size)")
@@ -179,7 +181,14 @@ def run_ours(a) -> dict:
         tr.train_step(it)
     ev1.record()
     sync()
-    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    my_ms = ev0.elapsed_time(ev1)
+    dev_ms = max_over_ranks(my_ms)
+    per_rank_ms = [my_ms / a.steps]
+    if world > 1:       # who is the slowest board?  (names the limiter of the 1 -> N curve)
+        t = torch.tensor([my_ms / a.steps], dtype=torch.float64, device=dev)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank_ms = [round(float(x.item()), 3) for x in allt]
     launches = _lib.launch_count()
     clocks = sampler.stop()
     outer_in_window = sum(1 for s in range(a.warmup + 1, a.warmup + a.steps + 1) if s % H == 0)
@@ -200,6 +209,14 @@ def run_ours(a) -> dict:
             times.append(max_over_ranks(e0.elapsed_time(e1)))
         outer_ms = min(times)
     nparam = model.arena.numel
+    # after an outer step every worker must hold bit-identical parameters: wrap-around integer checksum, min == max
+    params_equal = None
+    if world > 1 and tr.is_diloco:
+        fp = model.arena.master.view(torch.int32).sum(dtype=torch.int64)
+        pair = torch.stack([fp, -fp])
+        dist.all_reduce(pair, op=dist.ReduceOp.MAX)
+        params_equal = bool(int(pair[0]) == -int(pair[1]))
+        assert params_equal, "workers hold different parameters after the outer step"
 
     # ---------------- end-to-end arm: public API, pinned H2D every micro-batch, D2H loss read every step
     e2e = None
@@ -234,9 +251,11 @@ def run_ours(a) -> dict:
         "impl": "ours",
         "config": {"model": f"llama-{a.model}", "global_batch": a.batch * world, "per_worker_batch": a.batch,
                    "micro_batch": a.micro_batch, "grad_accum": accum, "seq_len": a.seq, "parallelism": f"diloco{world}x1",
-                   "local_steps": H, "outer_steps_in_timed_window": outer_in_window,
-                   "l2": "per-step working set (>10 GB activations + 3.4 GB optimizer state) >> 126 MB L2; no flush needed",
-                   "inner_opt": "AdamW lr4e-4 wd0.1 b(0.9,0.95) clip1.0 cosine(1000,88000)", "outer_opt": "SGD lr0.7 m0.9 nesterov"},
+                   "local_steps": H, "outer_steps_in_timed_window": outer_in_window},
+        "notes": {"l2": "per-step working set (>10 GB activations + 3.4 GB optimizer state) >> 126 MB L2; no flush needed",
+                  "inner_opt": "AdamW lr4e-4 wd0.1 b(0.9,0.95) clip1.0 cosine(1000,88000)", "outer_opt": "SGD lr0.7 m0.9 nesterov",
+                  "entry": "opendiloco_b200.trainer.DiLoCoTrainer.train_step"},
+        "per_rank_ms_per_step": per_rank_ms, "params_equal_across_ranks": params_equal,
         "tokens_per_sec_per_gpu": value / world,
         "mfu_vs_measured_sustained": (value / world) * flops_tok / (sustained * 1e12),
         "outer_sync_ms": outer_ms,
@@ -253,19 +272,22 @@ def run_ours(a) -> dict:
 def run_reference(a) -> dict:
     ref_dir = os.path.join(ROOT, "baseline", "_ref")
     if not os.path.isdir(os.path.join(ref_dir, "open_diloco")):
-        return {"impl": "reference", "unavailable": "baseline/_ref/open_diloco missing (pip --target install not present)"}
+        return {"impl": a.impl, "unavailable": "baseline/_ref/open_diloco missing (pip --target install not present)"}
     sys.path.insert(0, os.path.join(ROOT, "baseline"))
     try:
-        from run_reference import run as run_ref
+        if a.impl == "reference-fsdp":
+            from run_reference_fsdp import run as run_ref
+        else:
+            from run_reference import run as run_ref
     except Exception as e:  # pragma: no cover
-        return {"impl": "reference", "unavailable": f"reference shims failed to import: {type(e).__name__}: {e}"}
+        return {"impl": a.impl, "unavailable": f"reference shims failed to import: {type(e).__name__}: {e}"}
     try:
         return run_ref(a, ClockSampler)
     except Exception as e:
         import traceback
 
         traceback.print_exc()
-        return {"impl": "reference", "unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
+        return {"impl": a.impl, "unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
 
 
 def main():

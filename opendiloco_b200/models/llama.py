@@ -31,6 +31,11 @@ from .config import LlamaConfig
 IGNORE_INDEX = -100
 
 
+def _use_graph() -> bool:
+    return os.environ.get("ODB_CUDA_GRAPH", "0") == "1"
+
+
+
 @dataclass
 class CausalLMOutput:
     loss: torch.Tensor | None = None
@@ -112,13 +117,17 @@ class LlamaEngine:
         self.act_norms: dict[str, torch.Tensor] = {}
         self.module_hooks: dict[str, Any] = {}     # name -> holder module with user forward hooks
         self.head_grad_tmp: torch.Tensor | None = None
+        self._graphs: dict[tuple, dict] = {}       # (B, S, loss_scale, labels-alias) -> captured micro-step
 
     def workspace(self, B: int, S: int) -> _Workspace:
         key = (B, S, str(self.arena.device), self.arena.compute_dtype)
         ws = self._ws.get(key)
         if ws is None:
             if len(self._ws) >= 2:       # keep at most two shapes resident (train + eval)
-                self._ws.pop(next(iter(self._ws)))
+                old = next(iter(self._ws))
+                self._ws.pop(old)
+                for gk in [k for k in self._graphs if k[:2] == old[:2]]:      # graphs captured on the evicted buffers
+                    del self._graphs[gk]
             ws = _Workspace(self.cfg, B, S, self.arena.device, self.arena.compute_dtype, self.lce_chunk)
             self._ws[key] = ws
         return ws
@@ -344,6 +353,48 @@ class LlamaEngine:
         return loss
 
 
+    # --------------------------------------------------------------------------------------------- CUDA-graph replay
+    def forward_backward_graphed(self, ids: torch.Tensor, labels: torch.Tensor, loss_scale: float) -> torch.Tensor:
+        """``forward_backward`` with the ~250 launches of a micro-batch captured ONCE per (B, S, loss_scale) into a CUDA
+        graph and replayed afterwards (every buffer of the micro-step is static: workspace, arena, TMA descriptors are
+        baked kernel parameters).  Inputs are copied into the graph's static id / label buffers; the returned loss is the
+        graph's static output (consume it before the next replay).  Falls back to the eager path while hooks /
+        activation-norm collection are active (they run Python between kernels)."""
+        B, S = ids.shape
+        hooked = any(m._forward_hooks for m in self.module_hooks.values())
+        if self.collect_act_norms or hooked or not ids.is_cuda:
+            return self.forward_backward(ids, labels, loss_scale)
+        key = (B, S, float(loss_scale), labels is ids)
+        st = self._graphs.get(key)
+        if st is None:
+            st = {"calls": 0, "graph": None}
+            self._graphs[key] = st
+        if st["graph"] is None:
+            st["calls"] += 1
+            if st["calls"] <= 2:          # warm-up: allocations, cudaFuncSetAttribute, library handles
+                return self.forward_backward(ids, labels, loss_scale)
+            g_ids = torch.empty_like(ids)
+            g_lab = g_ids if labels is ids else torch.empty_like(labels)
+            g_ids.copy_(ids)
+            if g_lab is not g_ids:
+                g_lab.copy_(labels)
+            ws = self.workspace(B, S)
+            for l in range(self.cfg.num_hidden_layers):
+                ws.att[l] = ws.aux[l] = None
+            torch.cuda.synchronize(ids.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                loss = self.forward_backward(g_ids, g_lab, loss_scale)
+            st.update(graph=graph, ids=g_ids, labels=g_lab, loss=loss)
+            graph.replay()
+            return st["loss"]
+        st["ids"].copy_(ids, non_blocking=True)
+        if st["labels"] is not st["ids"]:
+            st["labels"].copy_(labels, non_blocking=True)
+        st["graph"].replay()
+        return st["loss"]
+
+
 class _NormOnly:
     """Stand-in handed to lm_head forward hooks: the logits are never materialised, only their L2 norm exists."""
 
@@ -492,6 +543,7 @@ class LlamaForCausalLM(nn.Module):
             if device != self.arena.device:
                 self.arena.migrate(device)
                 self.engine._ws.clear()
+                self.engine._graphs.clear()
                 self.engine.head_grad_tmp = None
                 self._rebind()
         return self
@@ -528,7 +580,10 @@ class LlamaForCausalLM(nn.Module):
 
     def forward_backward(self, input_ids: torch.Tensor, labels: torch.Tensor, loss_scale: float = 1.0,
                          attention_mask: torch.Tensor | None = None) -> torch.Tensor:
-        """Native fast path: one micro-batch forward+backward, grads += loss_scale * dL/dw. Returns the device loss."""
+        """Native fast path: one micro-batch forward+backward, grads += loss_scale * dL/dw. Returns the device loss.
+        With ODB_CUDA_GRAPH=1 (and no padding mask) the micro-step is replayed from a CUDA graph."""
+        if _use_graph() and attention_mask is None and input_ids.is_cuda and self.arena.compute_dtype == torch.bfloat16:
+            return self.engine.forward_backward_graphed(input_ids, labels, loss_scale)
         return self.engine.forward_backward(input_ids, labels, loss_scale, attention_mask)
 
     # ------------------------------------------------------------------ state dict / checkpoints

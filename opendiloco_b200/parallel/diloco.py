@@ -765,6 +765,8 @@ class DiLoCoOptimizer:
         n = self.num_peers
         if store is None or n <= 1:
             return None
+        if self.all_reduce_strategy == AllReduceStrategy.WAIT_FOR_ALL and self.timeout_waiting_for_peers is None:
+            return None                                  # handshake switched off (static swarm; kernel-time benchmarks)
         epoch, me = self.local_epoch, self.dht.rank_in_group
         self._inject_fault(epoch, me)
         window = float(self.timeout_waiting_for_peers if self.all_reduce_strategy == AllReduceStrategy.WAIT_FOR_ALL

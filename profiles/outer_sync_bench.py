@@ -30,7 +30,7 @@ from opendiloco_b200.parallel.swarm import DHT  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--models", default="150m,1b")
 ap.add_argument("--iters", type=int, default=5)
-ap.add_argument("--labels", default="fused_fp32,fused_bf16,nccl_flat_fp32,blockwise8bit")
+ap.add_argument("--labels", default="fused_fp32,fused_fp32_repl,fused_bf16,nccl_flat_fp32,blockwise8bit")
 ap.add_argument("--no-ref", action="store_true")
 a = ap.parse_args()
 
@@ -93,10 +93,13 @@ for name in a.models.split(","):
 
     # ------------------------------------------------------------------ ours (flat arena of the same size)
     row = {"model": name, "params": P, "n_gpus": world, "reference_ms": ref_min, "reference_GBps": 4 * P / ref_min / 1e6}
-    for label, comp, fused in [("fused_fp32", None, True), ("fused_bf16", "bf16", True), ("nccl_flat_fp32", None, False),
-                               ("blockwise8bit", "blockwise8bit", False)]:
+    # fused_fp32 = sharded in-place kernel (ZeRO-1 outer optimizer, all-reduce on the master weights themselves);
+    # fused_fp32_repl = the replicated-update pipelined kernel of round 1 (ODB_OUTER_SHARDED=0)
+    for label, comp, fused in [("fused_fp32", None, True), ("fused_fp32_repl", None, True), ("fused_bf16", "bf16", True),
+                               ("nccl_flat_fp32", None, False), ("blockwise8bit", "blockwise8bit", False)]:
         if label not in a.labels.split(","):
             continue
+        os.environ["ODB_OUTER_SHARDED"] = "0" if label == "fused_fp32_repl" else "1"
         flat = torch.nn.Parameter(torch.randn(((P + 16383) // 16384) * 16384, device=dev) * 0.02)
         opt = DiLoCoOptimizer(dht=DHT(start=True), batch_size=1, num_inner_steps=1, params=[flat],
                               outer_optimizer=partial(torch.optim.SGD, lr=0.7, momentum=0.9, nesterov=True),
@@ -117,6 +120,17 @@ for name in a.models.split(","):
         row[label + "_ms"] = t
         row[label + "_GBps"] = 4 * P / t / 1e6
         row[label + "_fused_kernel"] = used
+        if used:
+            row[label + "_mode"] = "sharded" if opt._fused.sharded else ("pipelined" if opt._fused.pipelined else "sequential")
+        if used and opt._fused.sharded:
+            # the background part of the sharded form: owners re-replicate their momentum slab (NCCL all-gather, side stream)
+            def regather():
+                opt._fused._regather_pending = True
+                opt._fused.start_momentum_regather()
+                opt._fused.wait_momentum()
+
+            regather()
+            row[label + "_background_momentum_regather_ms"] = timed(regather, 3)[0]
         if used and opt._fused.phase_times_us() is not None:
             row[label + "_phases_us"] = opt._fused.phase_times_us()
         opt.shutdown()

@@ -27,13 +27,37 @@ def test_forward_backward_matches_reference_path(shape):
     ids = torch.randint(3, cfg.vocab_size, (2, 128))
     lc = cpu.forward_backward(ids, ids, 1.0)
     lg = gpu.forward_backward(ids.cuda(), ids.cuda(), 1.0)
-    assert abs(lc.item() - lg.item()) < 2e-2
+    assert abs(lc.item() - lg.item()) < 5e-3
     gc, gg = cpu.arena.grad, gpu.arena.grad.cpu()
-    assert ((gc - gg).norm() / gc.norm()).item() < 5e-2
+    assert ((gc - gg).norm() / gc.norm()).item() < 2e-2
     # per-tensor check so one bad kernel cannot hide in the global norm
-    for name in cpu.arena.slots:
-        a, b = cpu.arena.g(name), gpu.arena.g(name).cpu()
-        assert ((a - b).norm() / (a.norm() + 1e-6)).item() < 0.12, name
+    worst = max((((cpu.arena.g(n) - gpu.arena.g(n).cpu()).norm() / (cpu.arena.g(n).norm() + 1e-6)).item(), n) for n in cpu.arena.slots)
+    print("worst per-tensor rel err vs the bf16 reference path:", worst)
+    assert worst[0] < 2e-2, worst
+
+
+@pytest.mark.parametrize("shape", ["150m_layer", "1b_gqa_layer"])
+def test_real_layer_shapes_against_fp32(shape):
+    """One decoder layer + embedding + LM head at the Llama-150M / Llama-1B (GQA 32:4) widths and the real vocabulary:
+    the bf16 kernel path against the SAME engine run in fp32 (PyTorch ops, fp32 master weights as compute weights)."""
+    if shape == "150m_layer":
+        cfg = LlamaConfig(hidden_size=1024, intermediate_size=2688, num_hidden_layers=1, num_attention_heads=16, vocab_size=32000)
+    else:
+        cfg = LlamaConfig(hidden_size=2048, intermediate_size=5632, num_hidden_layers=1, num_attention_heads=32,
+                          num_key_value_heads=4, vocab_size=32000)
+    ref = LlamaForCausalLM(cfg, device="cuda", precision="32-true", seed=2)
+    gpu = LlamaForCausalLM(cfg, device="cuda", precision="bf16-mixed", seed=2)
+    assert torch.equal(ref.arena.master, gpu.arena.master)
+    torch.manual_seed(3)
+    ids = torch.randint(3, cfg.vocab_size, (4, 512), device="cuda")
+    lr = ref.forward_backward(ids, ids, 1.0)
+    lg = gpu.forward_backward(ids, ids, 1.0)
+    assert abs(lr.item() - lg.item()) / lr.item() < 2e-3, (lr.item(), lg.item())
+    errs = {n: ((ref.arena.g(n) - gpu.arena.g(n)).norm() / (ref.arena.g(n).norm() + 1e-12)).item() for n in ref.arena.slots}
+    worst = max(errs.items(), key=lambda kv: kv[1])
+    print(shape, "worst per-tensor rel err vs fp32:", worst, " global:",
+          ((ref.arena.grad - gpu.arena.grad).norm() / ref.arena.grad.norm()).item())
+    assert worst[1] < 2e-2, errs                       # bf16 activations: a few 1e-3 per tensor is the rounding floor
 
 
 def test_autograd_facade_on_gpu():
