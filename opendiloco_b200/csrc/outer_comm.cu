@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(512) fused_outer_pipelined_kernel(
 // published done[c].  Entry barrier: every rank raises ready[0] when its kernel starts (stream order: its last AdamW step
 // is complete), and nobody reduces before all N have.
 template <int kDummy>
-__global__ void __launch_bounds__(512) fused_outer_sharded_kernel(
+__global__ void __launch_bounds__(512, 2) fused_outer_sharded_kernel(
     float* __restrict__ theta_outer, float* __restrict__ buf, float* theta_local, __nv_bfloat16* __restrict__ shadow,
     float* theta_mc, PeerPtrs flag_ptrs, int rank, int world, long long n, float lr, float mu, int nesterov, unsigned seq,
     unsigned launch_idx, int nchunk, int n_comm, PipeCounters* cnt, int* timeout_flag, long long* fingerprint) {
@@ -460,23 +460,22 @@ __global__ void __launch_bounds__(512) fused_outer_sharded_kernel(
     const long long cthreads = (long long)n_comm * blockDim.x;
     for (int c = 0; c < nchunk; ++c) {
       const long long lo = (long long)rank * slab4 + (long long)c * sub4, hi = lo + sub4;
-      constexpr int U = 4;
+      // U in-switch reductions in flight per thread (the NVLS round trip is microseconds: bytes in flight / latency is
+      // what bounds this phase); theta_outer / momentum are local and fetched only when the reduced value has arrived
+      constexpr int U = 6;
       for (long long i0 = lo + ctid; i0 < hi; i0 += cthreads * U) {
-        float4 sv[U], to[U], bb[U];
+        float4 sv[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const long long i = i0 + u * cthreads;
-          if (i < hi) {
-            sv[u] = multimem_ld_reduce_f32x4_weak(theta_mc + i * 4);
-            to[u] = ld_f4(theta_outer + i * 4);
-            bb[u] = ld_f4(buf + i * 4);
-          }
+          if (i < hi) sv[u] = multimem_ld_reduce_f32x4_weak(theta_mc + i * 4);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const long long i = i0 + u * cthreads;
           if (i < hi) {
-            float* T = &to[u].x; float* B = &bb[u].x; const float* S = &sv[u].x;
+            float4 to = ld_f4(theta_outer + i * 4), bb = ld_f4(buf + i * 4);
+            float* T = &to.x; float* B = &bb.x; const float* S = &sv[u].x;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float d = T[j] - S[j] * inv_world;
@@ -484,9 +483,9 @@ __global__ void __launch_bounds__(512) fused_outer_sharded_kernel(
               const float stp = nesterov ? (d + mu * B[j]) : B[j];
               T[j] -= lr * stp;
             }
-            st_f4(theta_outer + i * 4, to[u]);
-            st_f4(buf + i * 4, bb[u]);
-            multimem_st_f32x4_weak(theta_mc + i * 4, to[u]);
+            st_f4(theta_outer + i * 4, to);
+            st_f4(buf + i * 4, bb);
+            multimem_st_f32x4_weak(theta_mc + i * 4, to);
           }
         }
       }
@@ -550,7 +549,7 @@ ODB_EXPORT int odb_fused_outer_sharded(void* theta_outer, void* buf, void* theta
   if (e != cudaSuccess) return (int)e;
   if (per_sm < 1) return -3;
   const int grid = sm_count() * (per_sm > 2 ? 2 : per_sm);
-  if (n_comm <= 0 || n_comm >= grid) n_comm = grid / 2;
+  if (n_comm <= 0 || n_comm >= grid) n_comm = (2 * grid) / 3;
   float* a0 = (float*)theta_outer; float* a1 = (float*)buf; float* a2 = (float*)theta_local;
   __nv_bfloat16* a3 = (__nv_bfloat16*)shadow; float* a4 = (float*)theta_mc; int* tf = (int*)timeout_flag;
   PipeCounters* pc = (PipeCounters*)cnt; long long* fpr = (long long*)fingerprint;

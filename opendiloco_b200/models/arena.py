@@ -82,6 +82,10 @@ class ParamArena:
                 off += n
         self.used = off
         self.numel = (off + TOTAL_ALIGN - 1) // TOTAL_ALIGN * TOTAL_ALIGN
+        # FULL_SHARD / HYBRID_SHARD (ZeRO-3): between uses only this rank's slice of the compute weights is kept
+        self.param_group = None
+        self.shadow_shard: torch.Tensor | None = None
+        self.param_lo = self.param_hi = 0
         self._alloc(torch.device(device))
 
     # ------------------------------------------------------------------ storage
@@ -95,6 +99,7 @@ class ParamArena:
             self.shadow = torch.zeros(self.numel, dtype=self.compute_dtype, device=device)
 
     def migrate(self, device: torch.device) -> None:
+        assert self.param_group is None, "move the model before the optimizer shards its parameters"
         old_master, old_grad = self.master, self.grad
         self._alloc(device)
         self.master.copy_(old_master)
@@ -109,7 +114,43 @@ class ParamArena:
             self.shadow = buf
         self.master = buf
 
+    # ------------------------------------------------------------------ parameter sharding (FULL_SHARD / HYBRID_SHARD)
+    def enable_param_sharding(self, group, lo: int, hi: int) -> None:
+        """ZeRO-3 for the compute weights, with the reference's granularity: FSDP wraps the whole model in ONE unit
+        (train_fsdp.py:239-245, no auto-wrap policy), so the unit of gathering is the whole flat parameter - all-gathered
+        before forward, freed ("resharded") after it, all-gathered again before backward, freed after it.  Between uses a
+        rank holds only ``shadow_shard`` = its [lo, hi) slice (what the fused AdamW / outer kernels write)."""
+        if self.shadow is self.master:
+            return                                   # fp32 compute: the master weights are the compute weights
+        self.param_group, self.param_lo, self.param_hi = group, lo, hi
+        self.shadow_shard = self.shadow[lo:hi].clone()
+        self.shadow = None
+
+    @property
+    def param_sharded(self) -> bool:
+        return self.param_group is not None
+
+    def materialize_shadow(self) -> None:
+        """All-gather the full compute weights from the ranks' shards (no-op unless parameters are sharded)."""
+        if self.param_group is None or self.shadow is not None:
+            return
+        import torch.distributed as dist
+
+        full = torch.empty(self.numel, dtype=self.compute_dtype, device=self.device)
+        dist.all_gather_into_tensor(full, self.shadow_shard, group=self.param_group)
+        self.shadow = full
+
+    def release_shadow(self) -> None:
+        """Reshard: drop the gathered copy (the caching allocator gets the block back)."""
+        if self.param_group is not None:
+            self.shadow = None
+
     def sync_shadow(self) -> None:
+        if self.param_group is not None:
+            src = self.master[self.param_lo:self.param_hi]
+            K.cast_to_bf16(src, self.shadow_shard) if self.shadow_shard.dtype == torch.bfloat16 else self.shadow_shard.copy_(src)
+            self.shadow = None
+            return
         if self.shadow is not self.master:
             if self.shadow.dtype == torch.bfloat16:
                 K.cast_to_bf16(self.master, self.shadow)
@@ -125,7 +166,12 @@ class ParamArena:
         return self._view(self.master, name)
 
     def w(self, name: str) -> torch.Tensor:
-        return self._view(self.shadow, name)
+        return self._view(self._full_shadow(), name)
+
+    def _full_shadow(self) -> torch.Tensor:
+        if self.shadow is None:
+            raise RuntimeError("compute weights are sharded (FULL_SHARD): call arena.materialize_shadow() around their use")
+        return self.shadow
 
     def g(self, name: str) -> torch.Tensor:
         return self._view(self.grad, name)
@@ -135,13 +181,13 @@ class ParamArena:
         return buf[s.offset:s.offset + rows * cols].view(rows, cols)
 
     def qkv_w(self, l: int) -> torch.Tensor:
-        return self._fused(self.shadow, f"model.layers.{l}.self_attn.q_proj.weight", self.cfg.qkv_dim, self.cfg.hidden_size)
+        return self._fused(self._full_shadow(), f"model.layers.{l}.self_attn.q_proj.weight", self.cfg.qkv_dim, self.cfg.hidden_size)
 
     def qkv_g(self, l: int) -> torch.Tensor:
         return self._fused(self.grad, f"model.layers.{l}.self_attn.q_proj.weight", self.cfg.qkv_dim, self.cfg.hidden_size)
 
     def gu_w(self, l: int) -> torch.Tensor:
-        return self._fused(self.shadow, f"model.layers.{l}.mlp.gate_proj.weight", 2 * self.cfg.intermediate_size,
+        return self._fused(self._full_shadow(), f"model.layers.{l}.mlp.gate_proj.weight", 2 * self.cfg.intermediate_size,
                            self.cfg.hidden_size)
 
     def gu_g(self, l: int) -> torch.Tensor:

@@ -346,10 +346,16 @@ class LlamaEngine:
         B, S = ids.shape
         ws = self.workspace(B, S)
         mask = _normalize_mask(attention_mask)
+        ar = self.arena
         with torch.no_grad():
+            ar.materialize_shadow()            # FULL_SHARD: all-gather the compute weights (no-op otherwise)
             self.forward_hidden(ws, ids, mask)
             loss = self.head_loss(ws, labels, loss_scale, with_grad=True, direct=True)
+            if ar.param_sharded:               # reshard after forward, gather again for backward (FSDP FULL_SHARD)
+                ar.release_shadow()
+                ar.materialize_shadow()
             self.backward(ws, mask)
+            ar.release_shadow()
         return loss
 
 
@@ -459,8 +465,10 @@ class _EngineLoss(torch.autograd.Function):
         eng = model.engine
         B, S = ids.shape
         ws = eng.workspace(B, S)
+        eng.arena.materialize_shadow()
         eng.forward_hidden(ws, ids, mask)
         loss = eng.head_loss(ws, labels, 1.0, with_grad=True, direct=False)
+        eng.arena.release_shadow()
         ctx.model, ctx.ws, ctx.mask = model, ws, mask
         return loss.clone()
 
@@ -471,7 +479,9 @@ class _EngineLoss(torch.autograd.Function):
             g32 = g.to(torch.float32)
             ws.dxnf.mul_(g32.to(ws.dxnf.dtype))
             eng.arena.g("lm_head.weight").addcmul_(eng.head_grad_tmp, g32.expand_as(eng.head_grad_tmp))
+            eng.arena.materialize_shadow()
             eng.backward(ws, ctx.mask)
+            eng.arena.release_shadow()
         return None, None, None, None, None
 
 
@@ -573,16 +583,19 @@ class LlamaForCausalLM(nn.Module):
             return CausalLMOutput(loss=loss)
         with torch.no_grad():
             ws = eng.workspace(B, S)
+            self.arena.materialize_shadow()
             eng.forward_hidden(ws, input_ids, mask)
             loss = eng.head_loss(ws, labels, 1.0, with_grad=False, direct=False).clone() if labels is not None else None
             logits = eng.logits(ws).view(B, S, -1) if (return_logits or labels is None) else None
+            self.arena.release_shadow()
         return CausalLMOutput(loss=loss, logits=logits)
 
     def forward_backward(self, input_ids: torch.Tensor, labels: torch.Tensor, loss_scale: float = 1.0,
                          attention_mask: torch.Tensor | None = None) -> torch.Tensor:
         """Native fast path: one micro-batch forward+backward, grads += loss_scale * dL/dw. Returns the device loss.
         With ODB_CUDA_GRAPH=1 (and no padding mask) the micro-step is replayed from a CUDA graph."""
-        if _use_graph() and attention_mask is None and input_ids.is_cuda and self.arena.compute_dtype == torch.bfloat16:
+        if (_use_graph() and attention_mask is None and input_ids.is_cuda and self.arena.compute_dtype == torch.bfloat16
+                and not self.arena.param_sharded):
             return self.engine.forward_backward_graphed(input_ids, labels, loss_scale)
         return self.engine.forward_backward(input_ids, labels, loss_scale, attention_mask)
 

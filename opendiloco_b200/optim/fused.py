@@ -7,6 +7,9 @@
                      * ``shard=False`` (NO_SHARD): one flat gradient all-reduce (reference N3: FSDP NO_SHARD)
                      * ``shard=True``  (SHARD_GRAD_OP / _HYBRID_SHARD_ZERO2): flat reduce-scatter of gradients, AdamW on
                        the rank's slice of (master, m, v), all-gather of the bf16 compute weights (reference N4).
+                     * ``shard_params=True`` (FULL_SHARD / HYBRID_SHARD) additionally keeps the compute weights sharded
+                       between uses: the engine all-gathers them before forward and again before backward and frees the
+                       gathered copy after each (FSDP's reshard_after_forward on the reference's single flat unit).
 ``flatten_params`` re-homes arbitrary ``nn.Parameter``s into one contiguous fp32 buffer so every model, not only
                    the arena-backed Llama, gets the flat fast path.
 
@@ -34,6 +37,7 @@ class FlatView:
         self.params, self.flat, self.grad, self.offsets, self.shadow = params, flat, grad, offsets, shadow
         self.lo, self.hi = 0, flat.numel()
         self.shard_group = None
+        self.param_sharded = False           # FULL_SHARD: compute weights kept as per-rank shards between uses
         self.arena = getattr(params[0], "_odb_arena", None) if params else None
 
     @property
@@ -53,6 +57,21 @@ class FlatView:
     def own(self, buf: torch.Tensor | None) -> torch.Tensor | None:
         return None if buf is None else buf[self.lo:self.hi]
 
+    def own_shadow(self) -> torch.Tensor | None:
+        """This rank's slice of the low-precision compute weights (the persistent shard under FULL_SHARD)."""
+        if self.param_sharded:
+            return self.arena.shadow_shard
+        return self.own(self.shadow)
+
+    def shard_parameters(self) -> None:
+        """FULL_SHARD / HYBRID_SHARD on top of set_shard(): the gathered compute weights are released between uses."""
+        if self.arena is None or self.shadow is None or not self.sharded:
+            return
+        self.arena.enable_param_sharding(self.shard_group, self.lo, self.hi)
+        self.param_sharded = self.arena.param_sharded
+        if self.param_sharded:
+            self.shadow = None
+
     def view_of(self, buf: torch.Tensor, i: int) -> torch.Tensor:
         p = self.params[i]
         return buf[self.offsets[i]:self.offsets[i] + p.numel()].view(p.shape)
@@ -63,19 +82,38 @@ class FlatView:
         parameter view at it.  Values are preserved; optimizer moments / gradients are separate buffers and stay."""
         assert new_flat.numel() == self.flat.numel() and new_flat.dtype == self.flat.dtype and new_flat.device == self.flat.device
         new_flat.copy_(self.flat)
-        fp32_compute = self.shadow is None
+        fp32_compute = self.shadow is None and not self.param_sharded
         if self.arena is not None:
             self.arena.adopt_master(new_flat)
         self.flat = new_flat
         for p, o in zip(self.params, self.offsets):
             p.data = new_flat[o:o + p.numel()].view(p.shape)
-        assert fp32_compute == (self.shadow is None)
+        assert fp32_compute == (self.shadow is None and not self.param_sharded)
+
+    @torch.no_grad()
+    def rehome_grad(self, new_grad: torch.Tensor) -> None:
+        """Move the fp32 gradient accumulator into ``new_grad`` (a symmetric-memory window) and re-point ``p.grad``."""
+        assert new_grad.numel() == self.grad.numel() and new_grad.dtype == self.grad.dtype
+        new_grad.copy_(self.grad)
+        if self.arena is not None:
+            self.arena.grad = new_grad
+        self.grad = new_grad
+        for p, o in zip(self.params, self.offsets):
+            p.grad = new_grad[o:o + p.numel()].view(p.shape)
+
+    @torch.no_grad()
+    def rehome_shadow(self, new_shadow: torch.Tensor) -> None:
+        assert self.shadow is not None and new_shadow.numel() == self.shadow.numel() and new_shadow.dtype == self.shadow.dtype
+        new_shadow.copy_(self.shadow)
+        if self.arena is not None:
+            self.arena.shadow = new_shadow
+        self.shadow = new_shadow
 
     @torch.no_grad()
     def gather_compute_weights(self) -> None:
         """After a sharded update: every rank publishes its slice of the compute weights (bf16 shadow, or fp32 master
         when computing in fp32) to the worker's other GPUs."""
-        if not self.sharded:
+        if not self.sharded or self.param_sharded:      # FULL_SHARD gathers at the start of forward / backward instead
             return
         buf = self.shadow if self.shadow is not None else self.flat
         dist.all_gather_into_tensor(buf, buf[self.lo:self.hi], group=self.shard_group)
@@ -119,7 +157,8 @@ class FusedAdamW(torch.optim.Optimizer):
     HP_RING = 8
 
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2,
-                 max_grad_norm: float | None = None, zero_grad_in_step: bool = False, dp_group=None, shard: bool = False):
+                 max_grad_norm: float | None = None, zero_grad_in_step: bool = False, dp_group=None, shard: bool = False,
+                 shard_params: bool = False):
         params = list(params)
         if params and isinstance(params[0], dict):
             assert len(params) == 1, "FusedAdamW supports a single param group (the reference uses one)"
@@ -133,6 +172,8 @@ class FusedAdamW(torch.optim.Optimizer):
         self.dp_group = dp_group if (dp_group is not None and dist.get_world_size(dp_group) > 1) else None
         if self.dp_group is not None and shard:
             self.fv.set_shard(self.dp_group)
+            if shard_params:
+                self.fv.shard_parameters()
         fv = self.fv
         dev = fv.flat.device
         self.exp_avg = torch.zeros(fv.hi - fv.lo, dtype=torch.float32, device=dev)
@@ -157,6 +198,12 @@ class FusedAdamW(torch.optim.Optimizer):
         if arena is not None:
             arena.fused_optimizer = weakref.ref(self)                 # lets model.clip_grad_norm_() find us
         self._init_state_views()
+        # ZeRO-sharded worker on NVLink: reduce-scatter + clip + AdamW + all-gather as ONE kernel (csrc/zero_comm.cu)
+        self._zero = None
+        if self.dp_group is not None and self.fv.sharded and dev.type == "cuda":
+            from .zero_fused import FusedZeroStep
+
+            self._zero = FusedZeroStep.try_create(self)
 
     # ----------------------------------------------------------------- torch-compatible per-param state
     def _init_state_views(self) -> None:
@@ -201,7 +248,7 @@ class FusedAdamW(torch.optim.Optimizer):
     def sync_grads(self) -> None:
         """Average gradients over the worker's GPUs: flat all-reduce (NO_SHARD) or in-place flat reduce-scatter
         (ZeRO-2).  Idempotent per step; called by clip_grad_norm_ or step(), whichever comes first."""
-        if self.dp_group is None or self._grads_synced:
+        if self.dp_group is None or self._grads_synced or self._zero is not None:   # fused ZeRO: reduced inside the step kernel
             return
         fv = self.fv
         if fv.sharded:
@@ -234,6 +281,11 @@ class FusedAdamW(torch.optim.Optimizer):
     def compute_grad_norm_partials(self, max_norm: float) -> torch.Tensor:
         """Launch the norm pass now and remember it for the next step(); returns the (device) total norm lazily.
         Under a GradScaler the returned norm is that of the still-scaled gradients times 1/scale."""
+        if self._zero is not None:
+            # the fused ZeRO kernel reduces, measures and clips in one launch: only remember the threshold.  The returned
+            # tensor is the norm slot that launch fills (it holds the previous step's norm until then).
+            self._pending = (-1, float(max_norm))
+            return self.stats[0]
         self.sync_grads()
         n = self._norm_partials()
         self._pending = (n, float(max_norm))
@@ -303,16 +355,22 @@ class FusedAdamW(torch.optim.Optimizer):
         if self._pending is not None:
             n_part, max_norm = self._pending
             self._pending = None
+        elif self._zero is not None:
+            n_part = -1
         elif (max_norm is not None and max_norm > 0) or _check_inf:
             n_part = self._norm_partials()
         self._upload_hp({K.HP_LR: g["lr"], K.HP_B1: b1, K.HP_B2: b2, K.HP_EPS: g["eps"], K.HP_WD: g["weight_decay"],
                          K.HP_BC1: 1.0 - b1 ** self._step, K.HP_BC2: 1.0 - b2 ** self._step,
-                         K.HP_MAXNORM: max_norm if (max_norm is not None and max_norm > 0 and n_part > 0) else 0.0,
+                         K.HP_MAXNORM: max_norm if (max_norm is not None and max_norm > 0 and n_part != 0) else 0.0,
                          K.HP_INVSCALE: 1.0})
         if self._inv_scale is not None:           # device-side 1/scale (no host read of the GradScaler's scale)
             self._hp[K.HP_INVSCALE:K.HP_INVSCALE + 1].copy_(self._inv_scale.reshape(1))
             self._inv_scale = None
-        K.adamw_step(fv.own(fv.flat), fv.own(fv.grad), self.exp_avg, self.exp_avg_sq, fv.own(fv.shadow), self._hp,
+        if self._zero is not None:
+            self._zero.step(self._hp, _check_inf, self._flag, self.stats)       # gradients are zeroed by the kernel
+            self._grads_synced = False
+            return loss
+        K.adamw_step(fv.own(fv.flat), fv.own(fv.grad), self.exp_avg, self.exp_avg_sq, fv.own_shadow(), self._hp,
                      self._partials, n_part, self._flag if _check_inf else None, self.stats,
                      zero_grad=self.zero_grad_in_step and not fv.sharded)
         fv.gather_compute_weights()
@@ -324,7 +382,7 @@ class FusedAdamW(torch.optim.Optimizer):
     def zero_grad(self, set_to_none: bool = False) -> None:
         # gradients are views of the flat accumulator: keep them, zero in one op (reference: optimizer.zero_grad(),
         # train_fsdp.py:408).  With zero_grad_in_step the kernel already did it.
-        if not self.zero_grad_in_step:
+        if not self.zero_grad_in_step and self._zero is None:
             self.fv.grad.zero_()
         self._grads_synced = False
 

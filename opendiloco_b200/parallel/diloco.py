@@ -367,7 +367,7 @@ class DiLoCoStateAverager:
         self.fv = flat_view if flat_view is not None else flatten_params(self.main_parameters)
         dev = self.fv.flat.device if offload_device is None else torch.device(offload_device)
         self.theta_local = self.fv.own(self.fv.flat)          # the slice of the master weights this rank owns
-        self.shadow_local = self.fv.own(self.fv.shadow)
+        self.shadow_local = self.fv.own_shadow()
         self.theta_outer = self.theta_local.detach().to(dev, copy=True)
         self.delta = torch.zeros_like(self.theta_outer)
         self.momentum_buffer: torch.Tensor | None = None
@@ -786,14 +786,20 @@ class DiLoCoOptimizer:
             t_start = time.perf_counter()
             if order == 1:
                 deadline = t_start + window
+                everyone = False
                 while time.perf_counter() < deadline:
-                    if sum(store.check([k]) for k in keys) >= n - done_before:
+                    if done_before == 0 and store.check(keys):       # ONE round trip when the whole swarm is punctual
+                        everyone = True
+                        break
+                    if done_before > 0 and sum(store.check([k]) for k in keys) >= n - done_before:
                         break
                     # workers of a healthy swarm arrive within microseconds of each other: spin first, back off later
                     if time.perf_counter() - t_start > 0.002:
                         time.sleep(0.0005)
-                members = [q for q in range(n) if store.check([keys[q]])]
-                repair = any(store.get(keys[q]).decode() == "D" for q in members)
+                members = list(range(n)) if everyone else [q for q in range(n) if store.check([keys[q]])]
+                mkeys = [keys[q] for q in members]
+                marks = store.multi_get(mkeys) if hasattr(store, "multi_get") else [store.get(k) for k in mkeys]
+                repair = any(bytes(x).decode() == "D" for x in marks)
                 store.set(mkey, ",".join(str(q) for q in members) + "|" + ("1" if repair else "0"))
                 if len(members) < n - done_before:
                     logger.log(self.status_loglevel, f"Timeout waiting for peers, going to skip slowest peers; present={members}")

@@ -6,9 +6,10 @@ reduce-scattered and whose optimizer state is sharded.  Here that flat parameter
     NO_SHARD                          flat gradient all-reduce, replicated AdamW                (DDP-equivalent)
     SHARD_GRAD_OP, _HYBRID_SHARD_ZERO2 flat gradient reduce-scatter, AdamW on the rank's slice of (master, m, v,
                                       theta_outer, outer momentum), all-gather of the bf16 compute weights   (ZeRO-2)
-    FULL_SHARD, HYBRID_SHARD          same state sharding; the bf16 compute weights stay replicated: at 0.43 GB (150M) /
-                                      2.2 GB (1B) per GPU out of 180 GB, re-gathering them per layer would only add
-                                      NVLink traffic
+    FULL_SHARD, HYBRID_SHARD          same state sharding AND sharded compute weights (ZeRO-3): a rank keeps its slice of the
+                                      bf16 weights; the flat parameter is all-gathered before forward, freed after it,
+                                      all-gathered again before backward and freed after it - FSDP's behaviour for the
+                                      reference's single wrapping unit (``ParamArena.enable_param_sharding``)
 
 "HYBRID" (= shard inside a node, replicate across nodes) coincides with "shard inside a worker, DiLoCo across workers"
 in this framework's topology.  Implementation: ``optim.fused.FusedAdamW(dp_group=..., shard=...)``.
@@ -28,6 +29,10 @@ class ShardingStrategy(Enum):
     @property
     def shards_optimizer_state(self) -> bool:
         return self is not ShardingStrategy.NO_SHARD
+
+    @property
+    def shards_parameters(self) -> bool:
+        return self in (ShardingStrategy.FULL_SHARD, ShardingStrategy.HYBRID_SHARD)
 
 
 def get_sharding_strategy(sharding_strategy: str) -> ShardingStrategy:

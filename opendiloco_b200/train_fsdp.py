@@ -171,7 +171,8 @@ def train(config: Config) -> None:
     scaler = torch.amp.GradScaler(device.type, enabled=config.precision == "fp16-mixed")
 
     shard = config.sharding_strategy != "NO_SHARD"
-    inner_factory = partial(FusedAdamW, lr=config.lr, weight_decay=0.1, betas=(0.9, 0.95), dp_group=topo.inner_group, shard=shard)
+    inner_factory = partial(FusedAdamW, lr=config.lr, weight_decay=0.1, betas=(0.9, 0.95), dp_group=topo.inner_group, shard=shard,
+                            shard_params=config.sharding_strategy in ("FULL_SHARD", "HYBRID_SHARD"))
     scheduler_fn = partial(get_cosine_schedule_with_warmup, num_warmup_steps=config.warmup_steps,
                            num_training_steps=config.total_steps)
     ckpt_rank_dir = get_diloco_rank_dir_name(topo.world_rank) if hv is not None else ""

@@ -63,7 +63,7 @@ class DiLoCoTrainer:
         shard = cfg.sharding_strategy in SHARDED
         inner_factory = partial(FusedAdamW, lr=cfg.lr, weight_decay=cfg.weight_decay, betas=cfg.betas, eps=cfg.eps,
                                 max_grad_norm=cfg.max_grad_norm, zero_grad_in_step=True, dp_group=self.topo.inner_group,
-                                shard=shard)
+                                shard=shard, shard_params=cfg.sharding_strategy in ("FULL_SHARD", "HYBRID_SHARD"))
         sched_factory = partial(get_cosine_schedule_with_warmup, num_warmup_steps=cfg.warmup_steps,
                                 num_training_steps=cfg.total_steps)
         params = list(model.parameters())

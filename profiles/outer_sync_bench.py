@@ -101,6 +101,7 @@ for name in a.models.split(","):
             continue
         os.environ["ODB_OUTER_SHARDED"] = "0" if label == "fused_fp32_repl" else "1"
         flat = torch.nn.Parameter(torch.randn(((P + 16383) // 16384) * 16384, device=dev) * 0.02)
+        dist.broadcast(flat.data, src=0)          # workers of a real run start from identical weights (N1)
         opt = DiLoCoOptimizer(dht=DHT(start=True), batch_size=1, num_inner_steps=1, params=[flat],
                               outer_optimizer=partial(torch.optim.SGD, lr=0.7, momentum=0.9, nesterov=True),
                               inner_optimizer=partial(FusedAdamW, lr=0.0), grad_compression=get_compression(comp),

@@ -35,7 +35,7 @@ def torchrun(nproc: int, target: list[str], timeout: int = 900, extra_env: dict 
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout)
     if res.returncode != 0:
         pytest.fail(f"{' '.join(cmd)}\n{res.stdout[-4000:]}\n{res.stderr[-3000:]}")
-    return res.stdout
+    return res.stdout + "\n" + res.stderr
 
 
 @need(2)
@@ -131,3 +131,20 @@ def test_hybrid_two_workers_by_two_gpus_no_wait(tmp_path):
     torchrun(4, ["-m", "opendiloco_b200.train_fsdp"] + BASE + hv)
     losses = _load(f"{tmp_path}/log.pkl")
     assert len(losses) == 9 and all(np.isfinite(v[0]) for v in losses.values())
+
+
+@need(2)
+@pytest.mark.parametrize("sharding", ["SHARD_GRAD_OP", "FULL_SHARD"])
+def test_fused_zero_step_matches_the_nccl_path_2gpu(tmp_path, sharding):
+    """The one-kernel ZeRO step (in-switch reduce-scatter + clip + AdamW + multicast all-gather, csrc/zero_comm.cu) against
+    ncclReduceScatter + AdamW kernel + ncclAllGather on the same run: same losses."""
+    logs = {}
+    for mode in ("1", "0"):
+        logs[mode] = f"{tmp_path}/zero{mode}.pkl"
+        out = torchrun(2, ["-m", "opendiloco_b200.train_fsdp"] + BASE + ["--max_steps", "8", "--sharding_strategy", sharding,
+                                                                         "--project", logs[mode]], extra_env={"ODB_ZERO_FUSED": mode})
+        assert ("fused ZeRO step:" in out) == (mode == "1"), out[-2000:]
+    a, b = _load(logs["1"]), _load(logs["0"])
+    assert set(a) == set(b) == set(range(1, 9))
+    for s in a:
+        assert np.allclose(a[s][0], b[s][0], atol=2e-4), f"loss at step {s}: fused {a[s][0]} vs nccl {b[s][0]}"

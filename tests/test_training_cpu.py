@@ -38,7 +38,23 @@ def _load(path):
         return {d["step"]: (d["Loss"], d["lr"]) for d in pickle.load(f)}
 
 
-@pytest.mark.parametrize("sharding", ["NO_SHARD", "SHARD_GRAD_OP"])
+def test_full_shard_gathers_parameters_and_matches_zero2(tmp_path):
+    """FULL_SHARD (ZeRO-3: compute weights kept as per-rank shards, all-gathered for forward and again for backward) must
+    train exactly like SHARD_GRAD_OP (ZeRO-2): same kernels, same reduction order, only the residency of the weights
+    differs (reference: utils.py:138-152 -> FSDP ShardingStrategy)."""
+    logs = {}
+    for strat in ("SHARD_GRAD_OP", "FULL_SHARD", "HYBRID_SHARD"):
+        logs[strat] = f"{tmp_path}/{strat}.pkl"
+        torchrun(2, "opendiloco_b200.train_fsdp", BASE + ["--max_steps", "6", "--sharding_strategy", strat, "--project", logs[strat]])
+    a = _load(logs["SHARD_GRAD_OP"])
+    for strat in ("FULL_SHARD", "HYBRID_SHARD"):
+        b = _load(logs[strat])
+        assert set(a) == set(b) == set(range(1, 7))
+        for s in a:
+            assert a[s][0] == b[s][0], f"{strat}: loss at step {s}: {a[s][0]} vs {b[s][0]}"
+
+
+@pytest.mark.parametrize("sharding", ["NO_SHARD", "SHARD_GRAD_OP", "FULL_SHARD"])
 def test_ckpt_resume_data_parallel(tmp_path, sharding):
     ckpt = f"{tmp_path}/ckpt"
     log1, log2 = f"{tmp_path}/log1.pkl", f"{tmp_path}/log2.pkl"
