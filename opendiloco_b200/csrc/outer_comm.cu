@@ -564,6 +564,137 @@ ODB_EXPORT int odb_outer_set_timeout_ms(int ms) {
   return (int)cudaMemcpyToSymbol(g_outer_timeout_ns, &ns, sizeof(ns));
 }
 
+// =====================================================================================================================
+// Partial (elastic) round over the symmetric window: only the ranks listed in `members` take part - the workers that
+// missed the matchmaking window are neither waited for nor read.  Same three phases as fused_outer_kernel with peer
+// loads / stores (a multicast group spans all ranks, a subset cannot use it): member k of the round owns slice k of the
+// vector, sums the members' windows for it and writes the mean back into every member's window; every member then
+// applies Nesterov to its own full copy of theta_outer / momentum (the replicated outer state of an elastic swarm).
+struct Members {
+  int rank[kMaxPeers];
+};
+
+__device__ __forceinline__ void members_barrier(cg::grid_group& grid, const PeerPtrs& flag_ptrs, const Members& mem, int nm,
+                                                int rank, unsigned seq, int slot, int* timeout_flag) {
+  __threadfence_system();
+  grid.sync();
+  if (blockIdx.x == 0 && threadIdx.x < nm) {
+    const int peer = mem.rank[threadIdx.x];
+    st_release_sys(reinterpret_cast<unsigned*>(flag_ptrs.p[peer]) + slot * kMaxPeers + rank, seq);
+    spin_until_ge(reinterpret_cast<const unsigned*>(flag_ptrs.p[rank]) + slot * kMaxPeers + peer, seq, timeout_flag);
+  }
+  grid.sync();
+  __threadfence_system();
+}
+
+template <bool kBf16Delta>
+__global__ void __launch_bounds__(512) fused_outer_subset_kernel(float* __restrict__ theta_outer, float* __restrict__ buf,
+                                                                 float* __restrict__ theta_local, __nv_bfloat16* __restrict__ shadow,
+                                                                 void* sym_local, PeerPtrs sym_peers, PeerPtrs flag_ptrs, Members mem,
+                                                                 int nm, int my_idx, int rank, long long n, float lr, float mu,
+                                                                 int nesterov, unsigned seq, int* timeout_flag) {
+  cg::grid_group grid = cg::this_grid();
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  constexpr int VEC = kBf16Delta ? 8 : 4;
+  const long long nvec = n / VEC;
+  for (long long i = tid; i < nvec; i += nthreads) {
+    if constexpr (kBf16Delta) {
+      const float4 a0 = ld_f4(theta_outer + i * 8), a1 = ld_f4(theta_outer + i * 8 + 4);
+      const float4 b0 = ld_f4(theta_local + i * 8), b1 = ld_f4(theta_local + i * 8 + 4);
+      const float d[8] = {a0.x - b0.x, a0.y - b0.y, a0.z - b0.z, a0.w - b0.w, a1.x - b1.x, a1.y - b1.y, a1.z - b1.z, a1.w - b1.w};
+      st_v4(reinterpret_cast<__nv_bfloat16*>(sym_local) + i * 8, pack8(d));
+    } else {
+      const float4 a = ld_f4(theta_outer + i * 4), b = ld_f4(theta_local + i * 4);
+      st_f4(reinterpret_cast<float*>(sym_local) + i * 4, make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w));
+    }
+  }
+  members_barrier(grid, flag_ptrs, mem, nm, rank, seq, 0, timeout_flag);
+  if (*reinterpret_cast<volatile int*>(timeout_flag)) return;
+  const float inv = 1.f / (float)nm;
+  const long long per = (nvec + nm - 1) / nm;
+  const long long lo = per * my_idx, hi = (lo + per < nvec) ? lo + per : nvec;
+  for (long long i = lo + tid; i < hi; i += nthreads) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < nm; ++k) {
+      const int src = mem.rank[(my_idx + k) % nm];         // stagger the peers so the links are used evenly
+      if constexpr (kBf16Delta) {
+        float f[8];
+        unpack8(ld_vol_v4(reinterpret_cast<const __nv_bfloat16*>(sym_peers.p[src]) + i * 8), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      } else {
+        const float4 v = ld_vol_f4(reinterpret_cast<const float*>(sym_peers.p[src]) + i * 4);
+        acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= inv;
+    for (int k = 0; k < nm; ++k) {
+      const int dst = mem.rank[(my_idx + k) % nm];
+      if constexpr (kBf16Delta) st_v4(reinterpret_cast<__nv_bfloat16*>(sym_peers.p[dst]) + i * 8, pack8(acc));
+      else st_f4(reinterpret_cast<float*>(sym_peers.p[dst]) + i * 4, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    }
+  }
+  members_barrier(grid, flag_ptrs, mem, nm, rank, seq + 1, 1, timeout_flag);
+  if (*reinterpret_cast<volatile int*>(timeout_flag)) return;
+  for (long long i = tid; i < n / 4; i += nthreads) {
+    float4 d;
+    if constexpr (kBf16Delta) {
+      uint2 u;
+      asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(u.x), "=r"(u.y)
+                   : "l"(reinterpret_cast<const __nv_bfloat16*>(sym_local) + i * 4) : "memory");
+      const float2 a = bf2_to_f2(u.x), b = bf2_to_f2(u.y);
+      d = make_float4(a.x, a.y, b.x, b.y);
+    } else {
+      d = ld_vol_f4(reinterpret_cast<const float*>(sym_local) + i * 4);
+    }
+    float4 to = ld_f4(theta_outer + i * 4), bb = ld_f4(buf + i * 4);
+    float* T = &to.x; float* B = &bb.x; const float* D = &d.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      B[j] = mu * B[j] + D[j];
+      const float stp = nesterov ? (D[j] + mu * B[j]) : B[j];
+      T[j] -= lr * stp;
+    }
+    st_f4(theta_outer + i * 4, to);
+    st_f4(buf + i * 4, bb);
+    st_f4(theta_local + i * 4, to);
+    if (shadow) *reinterpret_cast<uint2*>(shadow + i * 4) = make_uint2(f2_to_bf2(to.x, to.y), f2_to_bf2(to.z, to.w));
+  }
+}
+
+// members: sorted ranks (inside the outer group) of this round, nm of them, this rank included.  n % 8 == 0.
+ODB_EXPORT int odb_fused_outer_subset(void* theta_outer, void* buf, void* theta_local, void* shadow, void* sym_local,
+                                      const void* const* sym_peers, const void* const* flag_ptrs, const int* members, int nm,
+                                      int rank, int world, long long n, float lr, float mu, int nesterov, unsigned seq,
+                                      int delta_bf16, void* timeout_flag, cudaStream_t st) {
+  if (world > kMaxPeers || nm < 2 || nm > world || n % 8) return -1;
+  PeerPtrs sp{}, fp{};
+  for (int i = 0; i < world; ++i) {
+    sp.p[i] = const_cast<void*>(sym_peers[i]);
+    fp.p[i] = const_cast<void*>(flag_ptrs[i]);
+  }
+  Members mem{};
+  int my_idx = -1;
+  for (int k = 0; k < nm; ++k) {
+    mem.rank[k] = members[k];
+    if (members[k] == rank) my_idx = k;
+  }
+  if (my_idx < 0) return -2;
+  void* fn = delta_bf16 ? (void*)fused_outer_subset_kernel<true> : (void*)fused_outer_subset_kernel<false>;
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 512, 0);
+  if (e != cudaSuccess) return (int)e;
+  if (per_sm < 1) return -3;
+  const int grid = sm_count() * (per_sm > 2 ? 2 : per_sm);
+  float* a0 = (float*)theta_outer; float* a1 = (float*)buf; float* a2 = (float*)theta_local;
+  __nv_bfloat16* a3 = (__nv_bfloat16*)shadow; int* tf = (int*)timeout_flag;
+  void* args[] = {&a0, &a1, &a2, &a3, &sym_local, &sp, &fp, &mem, &nm, &my_idx, &rank, &n, &lr, &mu, &nesterov, &seq, &tf};
+  e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(512), args, 0, st);
+  return (int)e;
+}
+
 // Pipelined launch (multimem only).  `cnt` = zero-initialised PipeCounters in device memory owned by the caller;
 // `launch_idx` = 1, 2, 3, ... ; `seq` as for the kernel above.  n % (8 * world * nchunk) must be 0.
 ODB_EXPORT int odb_fused_outer_pipelined(void* theta_outer, void* buf, void* theta_local, void* shadow, void* sym_local,

@@ -82,6 +82,7 @@ class ParamArena:
                 off += n
         self.used = off
         self.numel = (off + TOTAL_ALIGN - 1) // TOTAL_ALIGN * TOTAL_ALIGN
+        self.version = 0             # bumped whenever master / grad / shadow move to another allocation (graph invalidation)
         # FULL_SHARD / HYBRID_SHARD (ZeRO-3): between uses only this rank's slice of the compute weights is kept
         self.param_group = None
         self.shadow_shard: torch.Tensor | None = None
@@ -113,6 +114,7 @@ class ParamArena:
         if self.shadow is self.master:
             self.shadow = buf
         self.master = buf
+        self.version += 1
 
     # ------------------------------------------------------------------ parameter sharding (FULL_SHARD / HYBRID_SHARD)
     def enable_param_sharding(self, group, lo: int, hi: int) -> None:

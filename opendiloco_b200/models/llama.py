@@ -32,7 +32,10 @@ IGNORE_INDEX = -100
 
 
 def _use_graph() -> bool:
-    return os.environ.get("ODB_CUDA_GRAPH", "0") == "1"
+    """CUDA-graph replay of the micro-step (default on; ODB_CUDA_GRAPH=0 for the eager launch sequence).  Measured on B200,
+    Llama-150M: GPU busy 98.4 % -> 99.7 % of the step window (4052 inter-kernel gaps of ~2.2 us -> 193), +1.0 % tokens/s
+    (profiles/r2_idle_gap.txt)."""
+    return os.environ.get("ODB_CUDA_GRAPH", "1") == "1"
 
 
 
@@ -372,8 +375,10 @@ class LlamaEngine:
             return self.forward_backward(ids, labels, loss_scale)
         key = (B, S, float(loss_scale), labels is ids)
         st = self._graphs.get(key)
+        if st is not None and st.get("version") != self.arena.version:
+            st = None                     # an arena buffer was re-homed (symmetric-memory windows): captured pointers are stale
         if st is None:
-            st = {"calls": 0, "graph": None}
+            st = {"calls": 0, "graph": None, "version": self.arena.version}
             self._graphs[key] = st
         if st["graph"] is None:
             st["calls"] += 1

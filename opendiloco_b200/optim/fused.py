@@ -97,6 +97,7 @@ class FlatView:
         new_grad.copy_(self.grad)
         if self.arena is not None:
             self.arena.grad = new_grad
+            self.arena.version += 1
         self.grad = new_grad
         for p, o in zip(self.params, self.offsets):
             p.grad = new_grad[o:o + p.numel()].view(p.shape)
@@ -107,6 +108,7 @@ class FlatView:
         new_shadow.copy_(self.shadow)
         if self.arena is not None:
             self.arena.shadow = new_shadow
+            self.arena.version += 1
         self.shadow = new_shadow
 
     @torch.no_grad()

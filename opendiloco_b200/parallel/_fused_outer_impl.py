@@ -25,6 +25,8 @@ _lib.register_optional("odb_fused_outer_sharded", [c_void_p, c_void_p, c_void_p,
                                                   c_float, c_float, c_int, c_uint, c_uint, c_int, c_int, c_void_p, c_void_p,
                                                   c_void_p, c_void_p])
 _lib.register_optional("odb_outer_set_timeout_ms", [c_int])
+_lib.register_optional("odb_fused_outer_subset", [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                                 c_int, c_int, c_ll, c_float, c_float, c_int, c_uint, c_int, c_void_p, c_void_p])
 logger = get_logger()
 MAX_CHUNKS, MAX_PEERS = 64, 16
 FLAG_WORDS = 2 * MAX_CHUNKS * MAX_PEERS     # pipelined kernel: ready[chunk][peer] | done[chunk][peer]; phase-sequential kernel uses the first 32
@@ -64,7 +66,7 @@ class FusedOuterStep:
         self.timeout_flag = torch.zeros(1, dtype=torch.int32, device=dev)
         # ODB_OUTER_STAMPS=1: block 0 records globaltimer at the phase boundaries (phase profile of the fused kernel)
         self.stamps = torch.zeros(8, dtype=torch.int64, device=dev) if os.environ.get("ODB_OUTER_STAMPS") else None
-        self.seq = 1
+        self.seq = 0
         self.launch_idx = 0
         self.counters = torch.zeros(2 * MAX_CHUNKS, dtype=torch.int32, device=dev)
         self.nchunk = int(os.environ.get("ODB_OUTER_CHUNKS", 16))
@@ -145,11 +147,41 @@ class FusedOuterStep:
             logger.warning(f"fused outer step unavailable ({type(e).__name__}: {e}); using flat NCCL all-reduce + fused Nesterov")
             return None
 
+    def _seq_for(self, epoch: int | None) -> int:
+        """Sequence number of the cross-GPU flags of this round.  Derived from the OUTER EPOCH, not from a per-process launch
+        counter: the members of a round are at the same epoch by construction, whereas launch counts diverge as soon as a
+        worker sits out a partial round.  8 numbers per epoch: full round {0, 1}, partial rounds {2, 3}."""
+        if epoch is None:
+            self.seq += 8
+            return self.seq
+        self.seq = max(self.seq, 8 * (int(epoch) + 1))
+        return 8 * (int(epoch) + 1)
+
     @torch.no_grad()
-    def outer_step(self) -> None:
+    def outer_step_subset(self, members: list[int], epoch: int | None = None) -> None:
+        """Partial round: pseudo-gradient mean over ``members`` only (peer loads / stores on the symmetric window with a
+        member list - absent workers are neither waited for nor read), Nesterov on this rank's full outer state."""
+        sa = self.sa
+        g = sa._sgd_hparams()
+        self.wait_momentum()
+        arr = (c_int * len(members))(*members)
+        rc = _lib.cuda_lib().odb_fused_outer_subset(
+            sa.theta_outer.data_ptr(), sa.momentum_buffer.data_ptr(), sa.theta_local.data_ptr(),
+            sa.shadow_local.data_ptr() if sa.shadow_local is not None else None, self.window.data_ptr(), self._win_ptrs,
+            self._flag_ptrs, arr, len(members), self.rank, self.world, self.n, float(g["lr"]), float(g["momentum"]),
+            int(bool(g.get("nesterov", False))), self._seq_for(epoch) + 2, int(self.delta_bf16), self.timeout_flag.data_ptr(),
+            _lib.stream_ptr(sa.theta_outer))
+        _lib.check(rc, "fused_outer_subset")
+        _lib.count_launch()
+        self._arm_timeout_probe()
+        sa.fv.gather_compute_weights()
+
+    @torch.no_grad()
+    def outer_step(self, epoch: int | None = None) -> None:
         sa = self.sa
         g = sa._sgd_hparams()
         lib = _lib.cuda_lib()
+        seq = self._seq_for(epoch)
         if self.sharded:
             self.wait_momentum()            # the previous background all-gather reads the slab this launch rewrites
             self.launch_idx_sh += 1
@@ -158,12 +190,11 @@ class FusedOuterStep:
                 sa.theta_outer.data_ptr(), sa.momentum_buffer.data_ptr(), sa.theta_local.data_ptr(),
                 sa.shadow_local.data_ptr() if sa.shadow_local is not None else None, self._theta_mc, self._flag_ptrs,
                 self.rank, self.world, self.n, float(g["lr"]), float(g["momentum"]), int(bool(g.get("nesterov", False))),
-                self.seq, self.launch_idx_sh, self.nchunk_sh, int(os.environ.get("ODB_OUTER_COMM_CTAS", 0)),
+                seq, self.launch_idx_sh, self.nchunk_sh, int(os.environ.get("ODB_OUTER_COMM_CTAS", 0)),
                 self.counters_sh.data_ptr(), self.timeout_flag.data_ptr(), self.fingerprint.data_ptr(),
                 _lib.stream_ptr(sa.theta_outer))
             _lib.check(rc, "fused_outer_sharded")
             _lib.count_launch()
-            self.seq += 2
             self._arm_timeout_probe()
             self._regather_pending = True
             sa.fv.gather_compute_weights()
@@ -174,12 +205,11 @@ class FusedOuterStep:
                 sa.theta_outer.data_ptr(), sa.momentum_buffer.data_ptr(), sa.theta_local.data_ptr(),
                 sa.shadow_local.data_ptr() if sa.shadow_local is not None else None, self.window.data_ptr(), self.mc_ptr,
                 self._flag_ptrs, self.rank, self.world, self.n, float(g["lr"]), float(g["momentum"]),
-                int(bool(g.get("nesterov", False))), self.seq, self.launch_idx, self.nchunk,
+                int(bool(g.get("nesterov", False))), seq, self.launch_idx, self.nchunk,
                 int(os.environ.get("ODB_OUTER_COMM_CTAS", 0)), int(self.delta_bf16), self.counters.data_ptr(),
                 self.timeout_flag.data_ptr(), _lib.stream_ptr(sa.theta_outer))
             _lib.check(rc, "fused_outer_pipelined")
             _lib.count_launch()
-            self.seq += 2
             self._arm_timeout_probe()
             sa.fv.gather_compute_weights()
             return
@@ -187,12 +217,11 @@ class FusedOuterStep:
             sa.theta_outer.data_ptr(), sa.momentum_buffer.data_ptr(), sa.theta_local.data_ptr(),
             sa.shadow_local.data_ptr() if sa.shadow_local is not None else None, self.window.data_ptr(),
             self.mc_ptr if self.mc_ptr else None, self._win_ptrs, self._flag_ptrs, self.rank, self.world, self.n,
-            float(g["lr"]), float(g["momentum"]), int(bool(g.get("nesterov", False))), self.seq, int(self.delta_bf16),
+            float(g["lr"]), float(g["momentum"]), int(bool(g.get("nesterov", False))), seq, int(self.delta_bf16),
             self.timeout_flag.data_ptr(), int(os.environ.get("ODB_OUTER_P1_CTAS", 0)), int(os.environ.get("ODB_OUTER_MM_WEAK", 1)),
             self.stamps.data_ptr() if self.stamps is not None else None, _lib.stream_ptr(sa.theta_outer))
         _lib.check(rc, "fused_outer_step")
         _lib.count_launch()
-        self.seq += 2
         self._arm_timeout_probe()
         sa.fv.gather_compute_weights()
 

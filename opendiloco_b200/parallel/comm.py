@@ -42,7 +42,15 @@ def init_distributed(backend: str | None = None, init_method: str | None = None,
     if backend == "nccl":
         torch.cuda.set_device(local_rank)
         kwargs["device_id"] = torch.device("cuda", local_rank)
-    if init_method is not None:
+    if init_method is not None and init_method.startswith("tcp://"):
+        # Workers launched as SEPARATE torchrun jobs (run_training.sh) meet on one address.  The store is created here and
+        # not by init_process_group: under torchrun ``TORCHELASTIC_USE_AGENT_STORE`` makes torch's tcp:// handler connect
+        # to the address as a client on EVERY rank (it assumes the elastic agent hosts it), so nobody would ever listen.
+        host, port = init_method[len("tcp://"):].rsplit(":", 1)
+        store = dist.TCPStore(host, int(port), world_size, is_master=(rank == 0),
+                              timeout=datetime.timedelta(minutes=TIMEOUT_NCCL_MINUTES), wait_for_workers=False)
+        kwargs.update(store=store, rank=rank, world_size=world_size)
+    elif init_method is not None:
         kwargs.update(init_method=init_method, rank=rank, world_size=world_size)
     elif "RANK" not in os.environ:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")

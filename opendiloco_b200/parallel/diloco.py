@@ -924,13 +924,18 @@ class DiLoCoOptimizer:
             if members is not None and len(members) == 1:
                 # nobody else showed up in time: this worker's own pseudo-gradient is the round
                 sa.step(increment_epoch=True, optimizer_step=True, averaging_round=False, fused_solo=True)
+            elif members is not None and self._fused is not None and _lib_has("odb_fused_outer_subset"):
+                # partial round on the NVLink window: member-masked peer loads / stores, absent workers are not touched
+                self._fused.outer_step_subset(members, self.local_epoch)
+                sa.step(increment_epoch=True, optimizer_step=False, averaging_round=False)
+                self._fused.poll_timeout(block=False)
             elif members is not None:
                 ga.step(wait=True, timeout=self.averaging_timeout, control=self.scheduled_diloco_grads, members=members)
                 ga.notify_used_averaged_gradients()
                 self.scheduled_diloco_grads = None
                 sa.step(increment_epoch=True, optimizer_step=True, averaging_round=average_state, members=members)
             elif self._fused is not None:
-                self._fused.outer_step()                    # pseudo-grad + NVLink reduce + Nesterov in ONE kernel
+                self._fused.outer_step(self.local_epoch)   # pseudo-grad + NVLink reduce + Nesterov in ONE kernel
                 sa.step(increment_epoch=True, optimizer_step=False, averaging_round=average_state)
                 self._fused.poll_timeout(block=False)
             elif self.num_peers > 1:
@@ -1015,6 +1020,12 @@ class DiLoCoOptimizer:
         self.diloco_grad_averager.shutdown()
         if self._fused is not None:
             self._fused.close()
+
+
+def _lib_has(symbol: str) -> bool:
+    from .. import _lib
+
+    return _lib.has_symbol(symbol)
 
 
 def _accepts_kw(fn) -> bool:

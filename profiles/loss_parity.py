@@ -87,7 +87,15 @@ if a.impl == "reference":
     ref.load_dataset = lambda *args, **kwargs: FakeDatasetDict(train=Stream(), validation=Stream())
     ref.split_dataset_by_node = lambda ds, world_size, rank: ds
     ref.AutoTokenizer = type("_Tok", (), {"from_pretrained": staticmethod(lambda *x, **k: rr._local_tokenizer(vocab))})
-    ref.wandb.log = lambda d, *x, **k: (out.write(json.dumps({"step": int(d["step"]), "loss": float(d["Loss"])}) + "\n"), out.flush())
+    capture = lambda d, *x, **k: (out.write(json.dumps({"step": int(d["step"]), "loss": float(d["Loss"])}) + "\n"), out.flush())  # noqa: E731
+    stock_init = ref.wandb.init
+
+    def init_then_capture(*x, **k):        # wandb.init() re-binds wandb.log to the run's method: install the tap afterwards
+        r = stock_init(*x, **k)
+        ref.wandb.log = capture
+        return r
+
+    ref.wandb.init = init_then_capture
     ref.main(batch_size=a.batch, per_device_train_batch_size=a.batch, seq_length=a.seq, checkpoint_path="/tmp/odb_parity_ckpt",
              warmup_steps=a.warmup, total_steps=a.steps, precision="bf16-mixed", project="odb_parity", model_name_or_path=model_dir,
              lr=4e-4, local_steps=a.local_steps, outer_lr=0.7)

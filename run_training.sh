@@ -40,4 +40,11 @@ for i in $(seq 0 $(( N - 1 ))); do
         > "logs/log$i" 2>&1 &
     if [ "$i" -eq 0 ]; then sleep 2; fi
 done
+# DILOCO_WAIT=1: block until every worker has exited and return the first failure (CI / tests); default: follow worker 0's
+# log like the reference script does.
+if [ -n "${DILOCO_WAIT:-}" ]; then
+    rc=0
+    for pid in $(jobs -p); do wait "$pid" || rc=$?; done
+    exit $rc
+fi
 tail -f logs/log0

@@ -196,3 +196,21 @@ def test_swarm_runs_on_the_native_board(tmp_path):
         board.close()
     finally:
         server.stop()
+
+
+def test_run_training_sh_launches_two_workers(tmp_path):
+    """The launcher contract of the reference (open_diloco/run_training.sh:28-36): ``./run_training.sh <N> <gpus per worker>
+    <initial_peer|auto> [train_fsdp flags]`` starts N separate torchrun jobs that meet on one rendezvous address, each logging
+    to logs/log<i>.  Two CPU workers, 4 steps, one outer step."""
+    env = dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2", WANDB_MODE="disabled", DILOCO_WAIT="1",
+               DILOCO_PORT=str(free_port()))
+    args = [a for a in BASE if a != "16"]          # drop the DP total batch; DiLoCo: per-worker batch
+    args[args.index("--total_batch_size"):args.index("--total_batch_size") + 1] = ["--total_batch_size", "4"]
+    cmd = ["bash", os.path.join(ROOT, "run_training.sh"), "2", "1", "auto", *args, "--hv.local_steps", "2", "--max_steps", "4",
+           "--hv.skip_load_from_peers", "--hv.matchmaking_time", "1", "--project", f"{tmp_path}/log.pkl"]
+    res = subprocess.run(cmd, env=env, cwd=tmp_path, capture_output=True, text=True, timeout=240)
+    logs = {i: open(f"{tmp_path}/logs/log{i}").read() for i in (0, 1)}
+    assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-1500:] + logs[0][-2000:] + logs[1][-1500:]
+    assert "Training completed." in logs[0] and "Training completed." in logs[1]
+    assert "DiLoCo enabled: 2 workers x 1 GPU(s)" in logs[0]
+    assert set(_load(f"{tmp_path}/log.pkl")) == {1, 2, 3, 4}
