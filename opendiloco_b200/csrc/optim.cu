@@ -220,3 +220,37 @@ ODB_EXPORT int odb_nesterov_outer(void* theta_outer, void* buf, const void* delt
   ODB_CHECK_LAST();
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ state fingerprint
+// Wrap-around integer checksum of a buffer's 32-bit words (order independent, exact): the drift detector DiLoCo workers
+// exchange after a full outer round (two workers hold bit-identical theta_outer iff their checksums agree, up to 2^-64).
+// One pass at HBM speed; `out` (int64) is ACCUMULATED (zero it first).
+__global__ void __launch_bounds__(512) checksum_i32_kernel(const int4* __restrict__ buf, long long n4, unsigned long long* __restrict__ out) {
+  __shared__ long long sm[16];
+  long long s = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = ld_nc_v4(buf + i);
+    s += (long long)(int)v.x + (long long)(int)v.y + (long long)(int)v.z + (long long)(int)v.w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sm[w];
+    atomicAdd(out, (unsigned long long)t);
+  }
+}
+
+ODB_EXPORT int odb_checksum_i32(const void* buf, long long n_words, void* out, cudaStream_t st) {
+  if (n_words % 4) return -1;
+  const long long n4 = n_words / 4;
+  long long blocks = ceil_div_ll(n4, 512 * 8);
+  const long long cap = (long long)sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  checksum_i32_kernel<<<(int)blocks, 512, 0, st>>>((const int4*)buf, n4, (unsigned long long*)out);
+  ODB_CHECK_LAST();
+  return 0;
+}

@@ -441,8 +441,11 @@ template <int kDummy>
 __global__ void __launch_bounds__(512, 2) fused_outer_sharded_kernel(
     float* __restrict__ theta_outer, float* __restrict__ buf, float* theta_local, __nv_bfloat16* __restrict__ shadow,
     float* theta_mc, PeerPtrs flag_ptrs, int rank, int world, long long n, float lr, float mu, int nesterov, unsigned seq,
-    unsigned launch_idx, int nchunk, int n_comm, PipeCounters* cnt, int* timeout_flag, long long* fingerprint) {
+    unsigned launch_idx, int nchunk, int n_comm, PipeCounters* cnt, int* timeout_flag, long long* fingerprint,
+    unsigned long long* stamps) {
   const long long n4 = n / 4;                       // float4 vectors
+  // optional phase profile (globaltimer, ns): [0] start, [1] entry barrier passed, [2] comm CTA 0 done, [3] a post CTA done
+  if (stamps && blockIdx.x == 0 && threadIdx.x == 0) stamps[0] = globaltimer_ns();
   const long long slab4 = n4 / world;               // per owner
   const long long sub4 = slab4 / nchunk;            // per (owner, chunk)
   const float inv_world = 1.f / (float)world;
@@ -456,6 +459,7 @@ __global__ void __launch_bounds__(512, 2) fused_outer_sharded_kernel(
     if (threadIdx.x < world)
       st_release_sys(reinterpret_cast<unsigned*>(flag_ptrs.p[threadIdx.x]) + rank, seq);       // ready[0][rank] on every peer
     if (!wait_flags(my_flags, world, seq, timeout_flag)) return;
+    if (stamps && blockIdx.x == 0 && threadIdx.x == 0) stamps[1] = globaltimer_ns();
     const long long ctid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long cthreads = (long long)n_comm * blockDim.x;
     for (int c = 0; c < nchunk; ++c) {
@@ -498,6 +502,7 @@ __global__ void __launch_bounds__(512, 2) fused_outer_sharded_kernel(
         st_release_sys(reinterpret_cast<unsigned*>(flag_ptrs.p[threadIdx.x]) + DONE_OFF + c * kMaxPeers + rank, seq);
       }
     }
+    if (stamps && blockIdx.x == 0 && threadIdx.x == 0) stamps[2] = globaltimer_ns();
   } else {
     // ------------------------------------------------------------------------------- post CTAs: shadow + theta_outer refresh
     const int n_local = gridDim.x - n_comm;
@@ -518,6 +523,7 @@ __global__ void __launch_bounds__(512, 2) fused_outer_sharded_kernel(
         }
       }
     }
+    if (stamps && (int)blockIdx.x == n_comm && threadIdx.x == 0) stamps[3] = globaltimer_ns();
     if (fingerprint) {      // wrap-around integer checksum of the new theta (order independent): the drift detector
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) fp += __shfl_xor_sync(0xffffffffu, fp, o);
@@ -538,7 +544,7 @@ __global__ void __launch_bounds__(512, 2) fused_outer_sharded_kernel(
 ODB_EXPORT int odb_fused_outer_sharded(void* theta_outer, void* buf, void* theta_local, void* shadow, void* theta_mc,
                                        const void* const* flag_ptrs, int rank, int world, long long n, float lr, float mu,
                                        int nesterov, unsigned seq, unsigned launch_idx, int nchunk, int n_comm, void* cnt,
-                                       void* timeout_flag, void* fingerprint, cudaStream_t st) {
+                                       void* timeout_flag, void* fingerprint, void* stamps, cudaStream_t st) {
   if (world > kMaxPeers || nchunk > kMaxChunks || nchunk < 1 || theta_mc == nullptr) return -1;
   if (n % (4ll * world * nchunk)) return -2;
   PeerPtrs fp{};
@@ -553,8 +559,9 @@ ODB_EXPORT int odb_fused_outer_sharded(void* theta_outer, void* buf, void* theta
   float* a0 = (float*)theta_outer; float* a1 = (float*)buf; float* a2 = (float*)theta_local;
   __nv_bfloat16* a3 = (__nv_bfloat16*)shadow; float* a4 = (float*)theta_mc; int* tf = (int*)timeout_flag;
   PipeCounters* pc = (PipeCounters*)cnt; long long* fpr = (long long*)fingerprint;
+  unsigned long long* stp = (unsigned long long*)stamps;
   void* args[] = {&a0, &a1, &a2, &a3, &a4, &fp, &rank, &world, &n, &lr, &mu, &nesterov, &seq, &launch_idx, &nchunk, &n_comm,
-                  &pc, &tf, &fpr};
+                  &pc, &tf, &fpr, &stp};
   e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(512), args, 0, st);   // cooperative = all CTAs co-resident (they spin)
   return (int)e;
 }

@@ -347,6 +347,25 @@ def adamw_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tenso
         g.zero_()
 
 
+_lib.register_optional("odb_checksum_i32", [_ct.c_void_p, _ct.c_longlong, _ct.c_void_p, _ct.c_void_p])
+
+
+def checksum_i32(buf: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Wrap-around integer checksum of the 32-bit words of ``buf`` (int64 scalar tensor): exact and order independent, so
+    two workers hold bit-identical buffers iff the values agree.  CUDA: one pass at HBM speed; CPU: torch sum."""
+    if out is None:
+        out = torch.zeros(1, dtype=torch.int64, device=buf.device)
+    else:
+        out.zero_()
+    words = buf.view(torch.int32) if buf.element_size() == 4 else buf.view(torch.int16).to(torch.int32)
+    if buf.is_cuda and words.numel() % 4 == 0 and buf.element_size() == 4 and _lib.has_symbol("odb_checksum_i32"):
+        _lib.check(_lib.cuda_lib().odb_checksum_i32(_p(buf), words.numel(), _p(out), _lib.stream_ptr(buf)), "checksum_i32")
+        _lib.count_launch()
+    else:
+        out.add_(words.sum(dtype=torch.int64))
+    return out
+
+
 def pseudo_grad(theta_outer: torch.Tensor, theta_local: torch.Tensor, delta: torch.Tensor) -> torch.Tensor:
     """delta = theta_outer - theta_local (fp32 or bf16 out).  reference: train_diloco_torch.py:344, hivemind_diloco.py:166"""
     n = theta_outer.numel()

@@ -23,7 +23,7 @@ _lib.register_optional("odb_fused_outer_pipelined", [c_void_p, c_void_p, c_void_
                                                     c_void_p, c_void_p])
 _lib.register_optional("odb_fused_outer_sharded", [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll,
                                                   c_float, c_float, c_int, c_uint, c_uint, c_int, c_int, c_void_p, c_void_p,
-                                                  c_void_p, c_void_p])
+                                                  c_void_p, c_void_p, c_void_p])
 _lib.register_optional("odb_outer_set_timeout_ms", [c_int])
 _lib.register_optional("odb_fused_outer_subset", [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                                  c_int, c_int, c_ll, c_float, c_float, c_int, c_uint, c_int, c_void_p, c_void_p])
@@ -192,7 +192,7 @@ class FusedOuterStep:
                 self.rank, self.world, self.n, float(g["lr"]), float(g["momentum"]), int(bool(g.get("nesterov", False))),
                 seq, self.launch_idx_sh, self.nchunk_sh, int(os.environ.get("ODB_OUTER_COMM_CTAS", 0)),
                 self.counters_sh.data_ptr(), self.timeout_flag.data_ptr(), self.fingerprint.data_ptr(),
-                _lib.stream_ptr(sa.theta_outer))
+                self.stamps.data_ptr() if self.stamps is not None else None, _lib.stream_ptr(sa.theta_outer))
             _lib.check(rc, "fused_outer_sharded")
             _lib.count_launch()
             self._arm_timeout_probe()
@@ -272,6 +272,9 @@ class FusedOuterStep:
         if self.stamps is None:
             return None
         t = self.stamps.cpu().tolist()
+        if self.sharded:
+            return {"entry_barrier": (t[1] - t[0]) / 1e3, "owner_ctas(reduce+update+multicast)": (t[2] - t[1]) / 1e3,
+                    "post_cta_end_after_owner_end": (t[3] - t[2]) / 1e3, "total(block0 start -> post end)": (t[3] - t[0]) / 1e3}
         return {"phase0_delta": (t[1] - t[0]) / 1e3, "barrier0": (t[2] - t[1]) / 1e3, "phase1_reduce_bcast": (t[3] - t[2]) / 1e3,
                 "barrier1": (t[4] - t[3]) / 1e3, "phase2_nesterov(block0)": (t[5] - t[4]) / 1e3}
 

@@ -625,12 +625,11 @@ class DiLoCoOptimizer:
         group = self.dht.group if self.dht is not None else None
         if comm.group_size(group) <= 1 or sa.theta_outer.dtype != torch.float32:
             return
-        if self._fused is not None and self._fused.fingerprint is not None:
+        if self._fused is not None and self._fused.fingerprint is not None and self._fused.sharded:
             fp = self._fused.fingerprint.clone()                      # produced by the fused kernel's last pass
         else:
-            fp = sa.theta_outer.view(torch.int32).sum(dtype=torch.int64)
-            if sa.momentum_buffer is not None:
-                fp = fp + 3 * sa.momentum_buffer.view(torch.int32).sum(dtype=torch.int64)
+            # one pass over theta_outer at HBM speed (a momentum that drifted shows up in theta_outer one round later)
+            fp = K.checksum_i32(sa.theta_outer)
         pair = torch.stack([fp.reshape(()), -fp.reshape(())]).to(comm_device(group, fp.device))
         dist.all_reduce(pair, op=dist.ReduceOp.MAX, group=group)          # [max fp, -min fp]
         if pair.is_cuda:

@@ -134,10 +134,19 @@ def test_hybrid_two_workers_by_two_gpus_no_wait(tmp_path):
 
 
 @need(2)
+def test_fused_zero_step_kernel_matches_the_nccl_path():
+    """Kernel-level equivalence on identical weights / gradients (tests/dist_workers/zero_equiv.py): master slab, both Adam
+    moments, clip statistics, the bf16 weights on every rank and the zeroed gradient arena, ZeRO-2 and FULL_SHARD."""
+    n = 4 if NGPU >= 4 else 2
+    out = torchrun(n, [os.path.join(ROOT, "tests", "dist_workers", "zero_equiv.py")])
+    assert "FAIL" not in out and out.count("ALL OK") == n, out[-3000:]
+
+
+@need(2)
 @pytest.mark.parametrize("sharding", ["SHARD_GRAD_OP", "FULL_SHARD"])
-def test_fused_zero_step_matches_the_nccl_path_2gpu(tmp_path, sharding):
-    """The one-kernel ZeRO step (in-switch reduce-scatter + clip + AdamW + multicast all-gather, csrc/zero_comm.cu) against
-    ncclReduceScatter + AdamW kernel + ncclAllGather on the same run: same losses."""
+def test_training_with_the_fused_zero_step_2gpu(tmp_path, sharding):
+    """End to end through the CLI: the one-kernel ZeRO step is picked up (log line) and trains like the NCCL path (GPU
+    reductions are not bit-reproducible run to run - wgrad / norm partials accumulate with atomics - hence atol 1e-2)."""
     logs = {}
     for mode in ("1", "0"):
         logs[mode] = f"{tmp_path}/zero{mode}.pkl"
@@ -147,4 +156,4 @@ def test_fused_zero_step_matches_the_nccl_path_2gpu(tmp_path, sharding):
     a, b = _load(logs["1"]), _load(logs["0"])
     assert set(a) == set(b) == set(range(1, 9))
     for s in a:
-        assert np.allclose(a[s][0], b[s][0], atol=2e-4), f"loss at step {s}: fused {a[s][0]} vs nccl {b[s][0]}"
+        assert np.allclose(a[s][0], b[s][0], atol=1e-2), f"loss at step {s}: fused {a[s][0]} vs nccl {b[s][0]}"
