@@ -18,6 +18,7 @@
 #include <stdint.h>
 #include <string.h>
 #include <sys/socket.h>
+#include <sys/time.h>
 #include <unistd.h>
 
 #include <atomic>
@@ -160,6 +161,13 @@ struct Server {
         if (c >= 0) {
           int one = 1;
           ::setsockopt(c, IPPROTO_TCP, TCP_NODELAY, &one, sizeof(one));
+          // a client that stalls in the middle of a request must not freeze the single-threaded board: bound every
+          // blocking recv / send on the connection; a timed-out request drops that connection only
+          struct timeval tv;
+          tv.tv_sec = 2;
+          tv.tv_usec = 0;
+          ::setsockopt(c, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));
+          ::setsockopt(c, SOL_SOCKET, SO_SNDTIMEO, &tv, sizeof(tv));
           fds.push_back({c, POLLIN, 0});
         }
       }

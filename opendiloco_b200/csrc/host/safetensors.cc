@@ -131,7 +131,8 @@ ODB_API void* odb_st_open(const char* path) {
   f->data_off = 8 + hlen;
   if (!parse_header(*f, (const char*)f->map + 8, (size_t)hlen)) { f->error = "malformed header"; return f; }
   for (auto& t : f->tensors)
-    if (t.end < t.begin || f->data_off + t.end > f->size) { f->error = "tensor range outside file: " + t.name; break; }
+    // overflow-safe: compare against the payload size instead of adding the (attacker-controlled) offset to data_off
+    if (f->data_off > f->size || t.end < t.begin || t.end > f->size - f->data_off) { f->error = "tensor range outside file: " + t.name; break; }
   return f;
 }
 ODB_API const char* odb_st_error(void* h) { File* f = (File*)h; return f->error.empty() ? nullptr : f->error.c_str(); }

@@ -186,8 +186,9 @@ __global__ void __launch_bounds__(512) zero_step_kernel(float* __restrict__ p, f
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       float4 pp = ld_f4(p + (j + h) * 4);
+      const float4 gg = ld_f4(grad_local + (i + h) * 4);
+      st_f4(grad_local + (i + h) * 4, make_float4(0.f, 0.f, 0.f, 0.f));      // own slab: zeroed by the thread that consumed it
       if (!skip) {
-        const float4 gg = ld_f4(grad_local + (i + h) * 4);
         float4 mm = ld_f4(m + (j + h) * 4), vv = ld_f4(v + (j + h) * 4);
         float* P = &pp.x; float* M = &mm.x; float* V = &vv.x; const float* G = &gg.x;
 #pragma unroll
@@ -207,7 +208,11 @@ __global__ void __launch_bounds__(512) zero_step_kernel(float* __restrict__ p, f
     if (kShadow == 1 && !skip) mm_st_bf16x8(shadow_mc + (lo8 + k) * 8, pack8(w8));
     if (kShadow == 2 && !skip) st_v4(shadow_mc + k * 8, pack8(w8));          // shadow_mc = the local shard here
   }
-  for (long long i = tid; i < n4; i += nthreads) st_f4(grad_local + i * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+  // the other slabs were consumed by their owners in phase 1 (the norm exchange was the barrier): zero them here.  The own
+  // slab is NOT touched by this loop - other threads of this grid may still be reading it in the AdamW loop above.
+  for (long long i = tid; i < n4; i += nthreads) {
+    if (i < lo || i >= hi) st_f4(grad_local + i * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+  }
 
   // ---------------- exit: every owner's weights are on every rank
   world_barrier(grid, flags, 2, rank, world, seq, timeout_flag);

@@ -140,6 +140,8 @@ def save_checkpoint(checkpoint_path: str, model: torch.nn.Module, optimizer: tor
                          step=int(inner._step), param_groups=[{k: v for k, v in g.items() if k != "params"} for g in inner.param_groups])
             if diloco is not None:
                 sa = diloco.state_averager
+                if hasattr(diloco, "_sync_outer_state"):
+                    diloco._sync_outer_state()      # sharded fused outer step: wait for the background momentum all-gather
                 shard["theta_outer"] = sa.theta_outer.detach().cpu()
                 if sa.momentum_buffer is not None:
                     shard["outer_momentum"] = sa.momentum_buffer.detach().cpu()
@@ -163,21 +165,32 @@ def save_checkpoint(checkpoint_path: str, model: torch.nn.Module, optimizer: tor
         g["outer_optimizer"] = {"param_groups": sd["param_groups"],
                                 "state": {} if fv is not None else sd["state"]}   # flat tensors live in the shard files
     if diloco is not None:
-        g["diloco"] = {"local_epoch": diloco.local_epoch, "samples_accumulated": diloco.tracker.local_progress.samples_accumulated}
+        g["diloco"] = {"local_epoch": diloco.local_epoch, "samples_accumulated": diloco.tracker.local_progress.samples_accumulated,
+                       "drifted": bool(getattr(diloco, "_drifted", False))}
     if scaler is not None:
         g["scaler"] = scaler.state_dict()
     _save(g, os.path.join(checkpoint_path, GLOBAL_STATE_FILE))
 
 
 # ------------------------------------------------------------------------------------------------ load
+_SHARD_CACHE: dict[str, dict] = {}      # shard files of the checkpoint being loaded (cleared by load_checkpoint)
+
+
+def _load_shard(path: str) -> dict:
+    sh = _SHARD_CACHE.get(path)
+    if sh is None:
+        sh = _SHARD_CACHE[path] = _load(path)
+    return sh
+
+
 def _assemble(checkpoint_path: str, key: str, lo: int, hi: int, device) -> torch.Tensor | None:
-    """Collect flat range [lo, hi) of ``key`` from whichever shard files cover it."""
+    """Collect flat range [lo, hi) of ``key`` from whichever shard files cover it (every file is read once per load)."""
     fs = GenericFileSystem()
     files = [f for f in fs.ls(checkpoint_path, detail=False) if f.endswith(".distcp")]
     out = torch.empty(hi - lo, dtype=torch.float32)
     covered = 0
     for f in sorted(files):
-        sh = _load(f)
+        sh = _load_shard(f)
         if key not in sh:
             continue
         slo, shi = sh["lo"], sh["hi"]
@@ -199,6 +212,7 @@ def load_checkpoint(checkpoint_path: str, model: torch.nn.Module, optimizer: tor
     rank = int(os.environ.get("RANK", 0)) if rank is None else rank
     fv = _flat_view(optimizer)
     inner = _inner_of(optimizer)
+    _SHARD_CACHE.clear()
     if fv is not None:
         dev = fv.flat.device
         fv.flat[fv.lo:fv.hi].copy_(_assemble(checkpoint_path, "model", fv.lo, fv.hi, dev))
@@ -206,7 +220,7 @@ def load_checkpoint(checkpoint_path: str, model: torch.nn.Module, optimizer: tor
         if m is not None:
             inner.exp_avg.copy_(m)
             inner.exp_avg_sq.copy_(v)
-        first = _load(sorted(f for f in GenericFileSystem().ls(checkpoint_path, detail=False) if f.endswith(".distcp"))[0])
+        first = _load_shard(sorted(f for f in GenericFileSystem().ls(checkpoint_path, detail=False) if f.endswith(".distcp"))[0])
         inner._step = int(first.get("step", 0))
         # publish the restored weights to the compute copy (and to the worker's other GPUs when sharded)
         arena = getattr(model, "arena", None)
@@ -240,8 +254,10 @@ def load_checkpoint(checkpoint_path: str, model: torch.nn.Module, optimizer: tor
             outer_optimizer.load_state_dict(g["outer_optimizer"])
     if diloco is not None and "diloco" in g:
         diloco.state_averager.local_epoch = int(g["diloco"]["local_epoch"])
+        diloco._drifted = bool(g["diloco"].get("drifted", False))      # a resumed worker still asks for the drift repair
         diloco.tracker.update_epoch(diloco.local_epoch)
         diloco.tracker.report_local_progress(diloco.local_epoch, int(g["diloco"]["samples_accumulated"]))
     if scaler is not None and "scaler" in g:
         scaler.load_state_dict(g["scaler"])
+    _SHARD_CACHE.clear()
     return g["loss"]
