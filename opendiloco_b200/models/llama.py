@@ -396,7 +396,8 @@ class LlamaEngine:
             torch.cuda.synchronize(ids.device)
             graph = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
-            with torch.cuda.graph(graph):
+            # thread_local: the NCCL watchdog / data-loader threads keep making CUDA calls of their own during the capture
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 loss = self.forward_backward(g_ids, g_lab, loss_scale)
             # kernels of ours recorded in the graph: every replay launches them again (bench.py's gpu_launches book-keeping)
             st.update(graph=graph, ids=g_ids, labels=g_lab, loss=loss, kernels=_lib.launch_count() - n0)

@@ -177,12 +177,18 @@ class FusedOuterStep:
         sa.fv.gather_compute_weights()
 
     @torch.no_grad()
-    def outer_step(self, epoch: int | None = None) -> None:
+    def outer_step(self, epoch: int | None = None, replicated: bool = False) -> None:
+        """One full round.  ``replicated``: every rank applies the mean pseudo-gradient to ITS OWN theta_outer / momentum
+        (pipelined or phase-sequential kernel) - the form a drifted swarm needs, because a state-averaging round follows and
+        must see each worker's own update (hivemind semantics); the sharded form would hand everybody the slab owner's
+        state instead."""
         sa = self.sa
         g = sa._sgd_hparams()
         lib = _lib.cuda_lib()
         seq = self._seq_for(epoch)
-        if self.sharded:
+        if replicated:
+            self.wait_momentum()
+        if self.sharded and not replicated:
             self.wait_momentum()            # the previous background all-gather reads the slab this launch rewrites
             self.launch_idx_sh += 1
             self.fingerprint.zero_()

@@ -934,7 +934,8 @@ class DiLoCoOptimizer:
                 self.scheduled_diloco_grads = None
                 sa.step(increment_epoch=True, optimizer_step=True, averaging_round=average_state, members=members)
             elif self._fused is not None:
-                self._fused.outer_step(self.local_epoch)   # pseudo-grad + NVLink reduce + Nesterov in ONE kernel
+                # pseudo-grad + NVLink reduce + Nesterov in ONE kernel (replicated update when the state is about to be averaged)
+                self._fused.outer_step(self.local_epoch, replicated=average_state)
                 sa.step(increment_epoch=True, optimizer_step=False, averaging_round=average_state)
                 self._fused.poll_timeout(block=False)
             elif self.num_peers > 1:

@@ -15,6 +15,9 @@ timeout 400 $TR --master-port 29543 bench.py --gpus 8 --steps 4 --warmup 3 > gpu
 timeout 500 $TR --master-port 29544 bench.py --impl reference --gpus 8 --steps 3 --warmup 3 > gpurun_out/g_bench8_ref.json 2> gpurun_out/g_bench8_ref.err; tail -c 700 gpurun_out/g_bench8_ref.json
 # BASELINE config #3: 8 workers, H = 50 (two outer steps inside the timed window)
 timeout 600 $TR --master-port 29545 bench.py --gpus 8 --steps 100 --warmup 5 --local-steps 50 --no-e2e > gpurun_out/g_bench8_h50.json 2> gpurun_out/g_bench8_h50.err; tail -c 1500 gpurun_out/g_bench8_h50.json
+# BASELINE config #2 (H = 500) at a reduced batch (32 x 1024 tokens per worker-step, one micro-batch) so that 1000 steps and two
+# real 8-GPU outer syncs fit in a minute; the full-batch figure follows from ms/step and the outer sync time above
+timeout 400 $TR --master-port 29547 bench.py --gpus 8 --batch 32 --micro-batch 32 --steps 1000 --warmup 5 --local-steps 500 --no-e2e > gpurun_out/g_bench8_h500_b32.json 2> gpurun_out/g_bench8_h500_b32.err; tail -c 1200 gpurun_out/g_bench8_h500_b32.json
 # BASELINE config #4: Llama-1B, 4 DiLoCo workers x 2 GPUs (ZeRO-2 inside a worker: fused ZeRO step + fused outer step)
 timeout 500 $TR --master-port 29546 -m opendiloco_b200.train_fsdp --path-model 1b --fake-data --sharding-strategy _HYBRID_SHARD_ZERO2 \
   --per-device-train-batch-size 16 --total-batch-size 2048 --hv.local-steps 4 --hv.galaxy-size 4 --max-steps 9 \
