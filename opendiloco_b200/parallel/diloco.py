@@ -802,7 +802,7 @@ class DiLoCoOptimizer:
                 store.set(mkey, ",".join(str(q) for q in members) + "|" + ("1" if repair else "0"))
                 if len(members) < n - done_before:
                     logger.log(self.status_loglevel, f"Timeout waiting for peers, going to skip slowest peers; present={members}")
-                self._gc_round_keys(store, epoch - 2, n)
+                self._gc_due = epoch - 2                 # old round records are deleted after the round has been launched
                 return members, True, repair
             deadline = t_start + window + float(self.averaging_timeout or 60.0)
             while not store.check([mkey]):
@@ -953,6 +953,9 @@ class DiLoCoOptimizer:
                 self._fused.start_momentum_regather()    # background: owners publish their momentum slabs (side stream)
             if leader:
                 self._serve_resync_requests()
+                if getattr(self, "_gc_due", -1) >= 0:
+                    self._gc_round_keys(self.dht.store(), self._gc_due, self.num_peers)
+                    self._gc_due = -1
             if self.scheduled_state is not None and not self.scheduled_state.done():
                 self.scheduled_state.cancel()
             self.scheduled_state = None
