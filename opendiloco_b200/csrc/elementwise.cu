@@ -4,8 +4,6 @@
 //
 // Reference semantics (the reference delegates to HF transformers; see SURVEY.md §2.5 K1,K2,K4,K6):
 //   RMSNorm  modeling_llama.py:62-67    RoPE  modeling_llama.py:117-168    SwiGLU  modeling_llama.py:182-184
-#include <stdlib.h>
-
 #include "common.cuh"
 
 using namespace odb;
@@ -122,6 +120,10 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const __nv_bfloat16* x
 // dres (the gradient flowing down the residual stream) is updated in place: dres <- bf16(dres + dx).
 // If dres_in == nullptr the kernel writes dres = dx (used for the final norm, where no skip path exists).
 // Each warp keeps per-lane dw partial sums in registers across its rows; one smem reduction + atomics per CTA.
+// ncu: 59 % of the measured HBM copy bandwidth at h = 1024 (190 registers, one CTA per SM).  A column-owner rewrite (one
+// 8-column vector per thread, four rows in flight, row dots through shared memory, 126 registers) was measured in round 2
+// at 71 us against this kernel's 67 us per 32768 x 1024 call - the two block barriers per row group cost what the extra
+// occupancy bought - and was not kept.
 template <int NCH, bool kRegAcc>
 __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
                                                           const __nv_bfloat16* __restrict__ x,
@@ -228,89 +230,6 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const __nv_bfloat16* _
       }
     }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < h; i += blockDim.x) atomicAdd(&dw[i], sm_dw[i]);
-}
-
-// ---- column-owner variant for the model widths (h = 1024: 128 threads per row, h = 2048: 256).  A thread owns ONE 8-column
-// vector of every row it touches, so the dw partial sums are 8 registers (not 8 per 256 columns), w is loaded once, and
-// four rows per thread are in flight at once (12 independent 16-byte loads): ~3x the bytes in flight per SM of the
-// warp-per-row kernel above, which sat at 59 % of the HBM roofline with 190 registers (profiles/r2_ncu_bandwidth_*).
-template <int TPR>
-__global__ void __launch_bounds__(256) rmsnorm_bwd_cols_kernel(const __nv_bfloat16* __restrict__ dy,
-                                                               const __nv_bfloat16* __restrict__ x,
-                                                               const __nv_bfloat16* __restrict__ w,
-                                                               const float* __restrict__ rstd,
-                                                               const __nv_bfloat16* __restrict__ dres_in,
-                                                               __nv_bfloat16* __restrict__ dres_out,
-                                                               float* __restrict__ dw, int T, int h) {
-  constexpr int RS = 256 / TPR;          // rows side by side in the CTA
-  constexpr int U = 4;                   // rows in flight per thread
-  constexpr int WPR = TPR / 32;          // warps per row
-  extern __shared__ float sm_dw[];       // [h]
-  __shared__ float s_dot[U][RS][WPR];
-  const int c = threadIdx.x % TPR, slot = threadIdx.x / TPR, lane = threadIdx.x & 31, wir = c >> 5;
-  for (int i = threadIdx.x; i < h; i += blockDim.x) sm_dw[i] = 0.f;
-  float wv[8], acc[8];
-  unpack8(ld_v4(reinterpret_cast<const uint4*>(w) + c), wv);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  const float inv_h = 1.f / (float)h;
-  const int nvec = h / 8;                // == TPR
-  constexpr int ROWS = RS * U;
-  for (long long base = (long long)blockIdx.x * ROWS; base < T; base += (long long)gridDim.x * ROWS) {
-    uint4 rdy[U], rx[U], rres[U];
-    float r[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long t = base + u * RS + slot;
-      if (t < T) {
-        rdy[u] = ld_nc_v4(reinterpret_cast<const uint4*>(dy + (size_t)t * h) + c);
-        rx[u] = ld_nc_v4(reinterpret_cast<const uint4*>(x + (size_t)t * h) + c);
-        rres[u] = dres_in ? ld_v4(reinterpret_cast<const uint4*>(dres_in + (size_t)t * h) + c) : make_uint4(0, 0, 0, 0);
-        r[u] = rstd[t];
-      } else {
-        rdy[u] = rx[u] = rres[u] = make_uint4(0, 0, 0, 0);
-        r[u] = 0.f;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      float d[8], xv[8], part = 0.f;
-      unpack8(rdy[u], d);
-      unpack8(rx[u], xv);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh = xv[j] * r[u];
-        part += d[j] * wv[j] * xh;
-        acc[j] += d[j] * bf16_round(xh);
-      }
-      part = warp_sum(part);
-      if (lane == 0) s_dot[u][slot][wir] = part;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long t = base + u * RS + slot;
-      float dot = 0.f;
-#pragma unroll
-      for (int q = 0; q < WPR; ++q) dot += s_dot[u][slot][q];
-      dot *= inv_h;
-      if (t < T) {
-        float d[8], xv[8], p[8], o[8];
-        unpack8(rdy[u], d);
-        unpack8(rx[u], xv);
-        unpack8(rres[u], p);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = r[u] * (d[j] * wv[j] - xv[j] * r[u] * dot) + p[j];
-        st_v4(reinterpret_cast<uint4*>(dres_out + (size_t)t * h) + c, pack8(o));
-      }
-    }
-    __syncthreads();
-  }
-  (void)nvec;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) atomicAdd(&sm_dw[c * 8 + j], acc[j]);
   __syncthreads();
   for (int i = threadIdx.x; i < h; i += blockDim.x) atomicAdd(&dw[i], sm_dw[i]);
 }
@@ -477,15 +396,6 @@ ODB_EXPORT int odb_rmsnorm_bwd(const void* dy, const void* x, const void* w, con
                                void* dres_out, void* dw, int T, int h, cudaStream_t st) {
   if (h % 8) return -1;
   const size_t smem = (size_t)h * sizeof(float);
-  static const bool cols = getenv("ODB_RMSNORM_BWD_V1") == nullptr;
-  if (cols && (h == 1024 || h == 2048)) {
-    const int rows = (h == 1024 ? 2 : 1) * 4;
-    const int grid_c = grid_for(ceil_div(T, rows), 1, 3);
-    if (h == 1024) rmsnorm_bwd_cols_kernel<128><<<grid_c, 256, smem, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (const float*)rstd, (const __nv_bfloat16*)dres_in, (__nv_bfloat16*)dres_out, (float*)dw, T, h);
-    else rmsnorm_bwd_cols_kernel<256><<<grid_c, 256, smem, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (const float*)rstd, (const __nv_bfloat16*)dres_in, (__nv_bfloat16*)dres_out, (float*)dw, T, h);
-    ODB_CHECK_LAST();
-    return 0;
-  }
   const int grid = grid_for(T, 8, 2);
   ODB_DISPATCH_NCH(h, (rmsnorm_bwd_kernel<NCH, (NCH <= 8)><<<grid, 256, smem, st>>>(
                           (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (const float*)rstd,
