@@ -290,7 +290,6 @@ class LlamaEngine:
         cfg, ar = self.cfg, self.arena
         B, S, L = ws.B, ws.S, cfg.num_hidden_layers
         Hq, Hkv, D = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
-        h, i = cfg.hidden_size, cfg.intermediate_size
         K.rmsnorm_bwd(ws.dxnf, ws.xf, ar.w("model.norm.weight"), ws.rstdf, None, ws.dx, ar.g("model.norm.weight"))
         for l in reversed(range(L)):
             p = f"model.layers.{l}."

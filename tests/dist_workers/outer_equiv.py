@@ -1,7 +1,6 @@
 """Run under torchrun (nccl on GPUs, gloo on CPU).  Checks that N DiLoCo workers with different data reproduce the
 reference's outer-step semantics (train_diloco_torch.py:336-353: AVG of theta_outer-theta_local, Nesterov SGD, reset)
 for every transport: flat collective, fused symmetric-memory kernel (fp32 / bf16 window), compressed butterfly."""
-import copy
 import os
 import sys
 from functools import partial

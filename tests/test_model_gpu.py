@@ -3,7 +3,6 @@ import pytest
 import torch
 
 from opendiloco_b200 import DiLoCoTrainer, LlamaConfig, LlamaForCausalLM, TrainerConfig
-from opendiloco_b200.utils.data import SyntheticTokenLoader
 
 pytestmark = pytest.mark.gpu
 
