@@ -555,9 +555,10 @@ ODB_EXPORT int odb_fused_outer_sharded(void* theta_outer, void* buf, void* theta
   if (e != cudaSuccess) return (int)e;
   if (per_sm < 1) return -3;
   const int grid = sm_count() * (per_sm > 2 ? 2 : per_sm);
-  // owner CTAs: the NVLS round trips saturate with ~100 CTAs (8 GPUs: 120 -> 2.33 ms, 197 -> 2.54 ms, 250 -> 2.91 ms for the 860 MB
-  // vector; 2 GPUs: flat between 32 and 100); the rest of the grid runs the HBM-bound post pass
-  if (n_comm <= 0 || n_comm >= grid) n_comm = grid / 3 < 96 ? grid / 3 : 96;
+  // owner CTAs: the NVLS round trips saturate with well under 100 CTAs (860 MB vector, 8 GPUs: 64 -> 2.27 ms, 96 -> 2.34,
+  // 120 -> 2.33, 197 -> 2.54, 250 -> 2.91; 2 GPUs: flat between 32 and 100, 16 -> 4.3); the rest of the grid runs the
+  // HBM-bound post pass
+  if (n_comm <= 0 || n_comm >= grid) n_comm = grid / 3 < 64 ? grid / 3 : 64;
   float* a0 = (float*)theta_outer; float* a1 = (float*)buf; float* a2 = (float*)theta_local;
   __nv_bfloat16* a3 = (__nv_bfloat16*)shadow; float* a4 = (float*)theta_mc; int* tf = (int*)timeout_flag;
   PipeCounters* pc = (PipeCounters*)cnt; long long* fpr = (long long*)fingerprint;

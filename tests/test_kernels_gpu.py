@@ -249,3 +249,44 @@ def test_tcgen05_attention_backward_packed_rope():
     assert res is packed
     assert rel(packed, ref) < 6e-3       # dq is rotated in fp32 before its single bf16 rounding; the reference rounds twice
     assert torch.equal(packed[:, (Hq + Hkv) * 64:], dv)
+
+
+def test_grad_scaler_on_the_fused_kernel_path():
+    """fp16-mixed bookkeeping on the kernels (K11): 1/scale as device-side hyper-parameter, non-finite flag from the norm
+    pass, skipped update + halved scale on overflow (reference flow train_fsdp.py:390-405, utils.py:124-135)."""
+    import copy
+
+    from opendiloco_b200.optim.fused import FusedAdamW
+    from opendiloco_b200.utils.training import found_inf_grad
+
+    torch.manual_seed(0)
+    ours = torch.nn.Sequential(torch.nn.Linear(64, 128), torch.nn.Linear(128, 32)).to(DEV)
+    ref = copy.deepcopy(ours)
+    opt = FusedAdamW(ours.parameters(), lr=1e-2, betas=(0.9, 0.95), weight_decay=0.1, max_grad_norm=1.0)
+    ropt = torch.optim.AdamW(ref.parameters(), lr=1e-2, betas=(0.9, 0.95), weight_decay=0.1)
+    scaler = torch.amp.GradScaler("cuda", init_scale=2048.0, growth_interval=1000)
+    x = torch.randn(8, 64, device=DEV)
+    for _ in range(3):
+        scaler.scale(ours(x).pow(2).mean()).backward()
+        ref(x).pow(2).mean().backward()
+        torch.nn.utils.clip_grad_norm_(ref.parameters(), 1.0)
+        ropt.step()
+        ropt.zero_grad()
+        opt.unscale_(scaler)
+        opt.step_scaled(scaler)
+        assert not found_inf_grad(opt, scaler)
+        scaler.update()
+        opt.zero_grad()
+        for p, q in zip(ours.parameters(), ref.parameters()):
+            assert torch.allclose(p, q, atol=5e-6)
+    before = [p.detach().clone() for p in ours.parameters()]
+    scaler.scale(ours(x).pow(2).mean()).backward()
+    next(ours.parameters()).grad[0, 0] = float("inf")
+    opt.unscale_(scaler)
+    opt.step_scaled(scaler)
+    assert found_inf_grad(opt, scaler)
+    s0 = scaler.get_scale()
+    scaler.update()
+    assert scaler.get_scale() == s0 * 0.5
+    for p, q in zip(ours.parameters(), before):
+        assert torch.equal(p, q)
