@@ -34,6 +34,8 @@
 // B_MN = true: the B operand is stored [K, N] row-major (N contiguous, "MN-major"): C = A * B.  This is the dgrad form
 // dX = dY * W with W in its forward [out, in] layout, so no transposed weight copy is needed (the 64 x 64 boxes and the
 // LBO / SBO descriptor fields are the ones the weight-gradient kernel uses for both of its operands).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -50,7 +52,8 @@ constexpr int EPI_BYTES = BM * EPI_CHUNK * 2;  // 16 KB
 constexpr int THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue group 0, warps 6-9 epilogue group 1
 constexpr int EPI_THREADS = 128;      // per group
 constexpr int EPI_GROUPS = 2;
-constexpr int GROUP_M = 16;           // rasterisation: 16 m-blocks x all n-blocks per super-block (L2 reuse of A and B)
+constexpr int GROUP_M = 8;            // rasterisation: 8 m-blocks x all n-blocks per super-block (L2 reuse of A and B); measured
+                                      // 4 / 8 / 16 / 32 on the 150M layer shapes: 979 / 979 / 986 / 1018 us per layer (profiles/r2_gemm_raster.txt)
 constexpr uint32_t TMEM_COLS = 512;
 
 enum Epi { kStore = 0, kSwiGLU = 1, kRoPE = 2, kSwiGLUBwd = 3, kLCEFwd = 4, kLCEdX = 5 };
@@ -63,11 +66,19 @@ template <> struct Cfg<kSwiGLUBwd> { static constexpr int STAGES = 3, NBUF = 8; 
 template <int EPI>
 constexpr int smem_bytes() { return Cfg<EPI>::STAGES * (A_BYTES + B_BYTES) + Cfg<EPI>::NBUF * EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/; }
 
-__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& m_blk, int& n_blk) {
-  const int group_size = GROUP_M * num_n;
+// group_m > 0: groups of group_m m-blocks x all n-blocks, m fastest inside a group (A and B tiles of a group stay in L2).
+// group_m == 0: n fastest over the whole problem - for a few n-blocks and a very deep K (the LM-head dX: 4 n-blocks,
+// K = vocabulary) the pairs that share an A row-block then run side by side and the A operand is fetched from HBM once.
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int group_m, int& m_blk, int& n_blk) {
+  if (group_m == 0) {
+    m_blk = tile / num_n;
+    n_blk = tile - m_blk * num_n;
+    return;
+  }
+  const int group_size = group_m * num_n;
   const int group_id = tile / group_size;
-  const int first_m = group_id * GROUP_M;
-  const int gsz = (num_m - first_m) < GROUP_M ? (num_m - first_m) : GROUP_M;
+  const int first_m = group_id * group_m;
+  const int gsz = (num_m - first_m) < group_m ? (num_m - first_m) : group_m;
   const int r = tile - group_id * group_size;
   m_blk = first_m + r % gsz;
   n_blk = r / gsz;
@@ -76,6 +87,7 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int&
 struct Params {
   int M, N, K;
   int num_m, num_n;          // tile counts
+  int group_m;               // rasterisation (see tile_coords)
   int I;                     // kSwiGLU: intermediate size (row offset of the up projection inside B, column offset in C)
   int S, rope_cols;          // kRoPE: sequence length, number of leading columns that get rotated
   const float* cos_t;        // [S, 32] fp32 (head_dim 64)
@@ -153,7 +165,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         int m_blk, n_blk;
-        tile_coords(tile, p.num_m, p.num_n, m_blk, n_blk);
+        tile_coords(tile, p.num_m, p.num_n, p.group_m, m_blk, n_blk);
         const int m_idx = m_blk * (2 * BM) + (int)cta_rank * BM;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -224,7 +236,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       int m_blk, n_blk;
-      tile_coords(tile, p.num_m, p.num_n, m_blk, n_blk);
+      tile_coords(tile, p.num_m, p.num_n, p.group_m, m_blk, n_blk);
       const int m_idx = m_blk * (2 * BM) + (int)cta_rank * BM;
       const uint32_t leader_tmem_empty = mapa_shared(smem_u32(&tmem_empty[acc]), 0);
       if constexpr (EPI == kSwiGLUBwd) {
@@ -564,6 +576,13 @@ static int launch(const void* A, const void* B, void* C, void* aux, int M, int N
   p.M = M; p.N = N; p.K = K;
   p.num_m = ceil_div(M, 2 * BM);
   p.num_n = (EPI == kSwiGLU) ? ceil_div(I, BN / 2) : ceil_div(N, BN);
+  {
+    static int env_group = -2, env_dx = -2;
+    if (env_group == -2) { const char* e = getenv("ODB_GEMM_GROUP_M"); env_group = e ? atoi(e) : -1; }
+    if (env_dx == -2) { const char* e = getenv("ODB_LCE_DX_GROUP_M"); env_dx = e ? atoi(e) : -1; }
+    p.group_m = env_group >= 0 ? env_group : GROUP_M;
+    if (EPI == kLCEdX) p.group_m = env_dx >= 0 ? env_dx : 0;      // n fastest: 1491 -> 1415 us at T = 32768, V = 32000
+  }
   p.I = I; p.S = S > 0 ? S : 1; p.rope_cols = rope_cols; p.cos_t = cos_t; p.sin_t = sin_t;
   p.ks1 = sp.K0 ? sp.K0 / BK : 0;
   p.ks2 = sp.K0 ? (sp.K0 + sp.K1) / BK : 0;

@@ -79,9 +79,9 @@ for (M, I, Kd) in [(32768, 2688, 1024), (16384, 5632, 2048)]:
     gu = torch.randn(M, 2 * I, device=dev).to(BF)
     dact = torch.empty(M, I, device=dev, dtype=BF)
     ref = K.swiglu_bwd(T.linear(dy, wt, dact), gu)
-    fused = gu.clone(); T.linear_swiglu_bwd(dy, wt, fused); torch.cuda.synchronize()
+    fused = gu.clone(); T.linear_swiglu_bwd_t(dy, wt, fused); torch.cuda.synchronize()
     work = gu.clone()
-    t1 = timeit(lambda: T.linear_swiglu_bwd(dy, wt, work))
+    t1 = timeit(lambda: T.linear_swiglu_bwd_t(dy, wt, work))
     t0 = timeit(lambda: (torch.mm(dy, wt.t(), out=dact), K.swiglu_bwd(dact, work, work)))
     t2 = timeit(lambda: (T.linear(dy, wt, dact), K.swiglu_bwd(dact, work, work)))
     print(f"M{M} I{I} K{Kd}: err vs unfused {rel(fused, ref):.2e}  fused {t1*1e3:.1f}us | cublas+kernel {t0*1e3:.1f}us | own gemm+kernel {t2*1e3:.1f}us | ratio {t0/t1:.2f}")
