@@ -124,6 +124,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   // Each CTA owns TWO key tiles of one (batch, kv head): tile x (nq-x query tiles to visit) and tile nq-1-x (x+1), so every
   // CTA runs group*(nq+1) iterations - a balanced grid - and pays the fixed costs once.  `it` is the CTA-wide iteration
   // index all per-iteration barrier parities derive from.
+  pdl_launch_dependents();
   const int kb_first = (int)blockIdx.x, kb_second = nq - 1 - (int)blockIdx.x;
   const int nitems = kb_first != kb_second ? 2 : 1;
   const int hk = blockIdx.y, b = blockIdx.z;
@@ -152,6 +153,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   tc_fence_after_sync();
   const uint32_t tb = *tmem_slot;
   const uint32_t tS = tb, tdP = tb + 128, tdV = tb + 256, tdK = tb + 320, tdQ = tb + 384;
+  pdl_wait();
 
   // register file split per warpgroup (EWS = 2: 128 threads x {96, 160, 160, 96}; EWS = 4: 80 at launch -> {64, 88 x 4, 64})
   // (each setmaxnreg sits inside its role branch and the branches only re-join at the final barrier, so ptxas allocates
@@ -459,6 +461,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
 __global__ void __launch_bounds__(256) attn_dsum_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
                                                         const float* __restrict__ lse, float* __restrict__ stats,
                                                         float* __restrict__ dq_acc, int B, int S, int Hq, long long ld, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)B * S * Hq * 8;
   if (i >= total) return;                                // total is a multiple of 8: whole lane groups leave together
@@ -493,6 +497,8 @@ __global__ void __launch_bounds__(256) attn_bwd_finish_kernel(const float* __res
                                                               __nv_bfloat16* __restrict__ dk, const float* __restrict__ cos_t,
                                                               const float* __restrict__ sin_t, long long T, int S, int Hq, int Hkv,
                                                               long long ld_out, long long ld_dk) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int H = Hq + (cos_t != nullptr ? Hkv : 0);
   const long long total = T * H * 4;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -553,9 +559,8 @@ ODB_EXPORT int odb_attn_bwd(const void* qkv, const void* out, const void* dout, 
   const long long T = (long long)B * S;
   {
     const long long threads = T * Hq * 8;
-    attn_dsum_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)out,
-                                                                        (const float*)lse, (float*)stats, (float*)dq_acc, B, S, Hq,
-                                                                        ld_out, softmax_scale);
+    launch_pdl(attn_dsum_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, st, (const __nv_bfloat16*)dout,
+               (const __nv_bfloat16*)out, (const float*)lse, (float*)stats, (float*)dq_acc, B, S, Hq, ld_out, softmax_scale);
   }
   CUtensorMap tq, tdo, tdq, tdk, tdv;
   int rc;
@@ -579,13 +584,12 @@ ODB_EXPORT int odb_attn_bwd(const void* qkv, const void* out, const void* dout, 
     if (e != cudaSuccess) { ews = 0; return (int)e; }
   }
   dim3 grid((S / BKV + 1) / 2, Hkv, B);
-  if (ews == 2) attn_bwd_kernel<2><<<grid, Roles<2>::THREADS, SMEM_BYTES, st>>>(tq, tdo, tdq, tdk, tdv, p);
-  else attn_bwd_kernel<4><<<grid, Roles<4>::THREADS, SMEM_BYTES, st>>>(tq, tdo, tdq, tdk, tdv, p);
+  if (ews == 2) launch_pdl(attn_bwd_kernel<2>, grid, dim3(Roles<2>::THREADS), SMEM_BYTES, st, tq, tdo, tdq, tdk, tdv, p);
+  else launch_pdl(attn_bwd_kernel<4>, grid, dim3(Roles<4>::THREADS), SMEM_BYTES, st, tq, tdo, tdq, tdk, tdv, p);
   {
     const long long threads = T * (Hq + (cos_t ? Hkv : 0)) * 4;
-    attn_bwd_finish_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((const float*)dq_acc, (__nv_bfloat16*)dq,
-                                                                              (__nv_bfloat16*)dk, (const float*)cos_t,
-                                                                              (const float*)sin_t, T, S, Hq, Hkv, ld_dq, ld_dkv);
+    launch_pdl(attn_bwd_finish_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, st, (const float*)dq_acc,
+               (__nv_bfloat16*)dq, (__nv_bfloat16*)dk, (const float*)cos_t, (const float*)sin_t, T, S, Hq, Hkv, ld_dq, ld_dkv);
   }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;

@@ -63,6 +63,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   uint64_t* q_empty = o_done + 1;               // every QK^T of the current query tile retired: Q may be replaced
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_empty + 1);
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nq = p.S / BQ;
   // Each CTA owns TWO query tiles of one (batch, head): tile nq-1-x (long) and tile x (short).  Every CTA therefore
@@ -95,6 +96,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tO = tmem_base + 128, tP = tmem_base + 192;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -343,7 +345,7 @@ ODB_EXPORT int odb_attn_fwd(const void* qkv, void* out, void* lse, int B, int S,
     attr_set = true;
   }
   dim3 grid((S / BQ + 1) / 2, Hq, B);
-  attn_fwd_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tq, to, p);
+  launch_pdl(attn_fwd_kernel, grid, dim3(THREADS), SMEM_BYTES, st, tq, to, p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }

@@ -13,6 +13,8 @@ using namespace odb;
 __global__ void __launch_bounds__(256) embedding_fwd_kernel(const long long* __restrict__ ids,
                                                             const __nv_bfloat16* __restrict__ W,
                                                             __nv_bfloat16* __restrict__ out, int T, int h) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   for (int t = blockIdx.x * warps_per_block + (threadIdx.x >> 5); t < T; t += gridDim.x * warps_per_block) {
@@ -27,6 +29,8 @@ __global__ void __launch_bounds__(256) embedding_fwd_kernel(const long long* __r
 __global__ void __launch_bounds__(256) embedding_bwd_kernel(const long long* __restrict__ ids,
                                                             const __nv_bfloat16* __restrict__ dout,
                                                             float* __restrict__ dW, int T, int h, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   for (int t = blockIdx.x * warps_per_block + (threadIdx.x >> 5); t < T; t += gridDim.x * warps_per_block) {
@@ -51,6 +55,8 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const __nv_bfloat16* x
                                                           const __nv_bfloat16* __restrict__ w,
                                                           __nv_bfloat16* __restrict__ y, float* __restrict__ rstd_out,
                                                           int T, int h, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int nvec = h / 8;
@@ -132,6 +138,8 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const __nv_bfloat16* _
                                                           const __nv_bfloat16* __restrict__ dres_in,
                                                           __nv_bfloat16* __restrict__ dres_out,
                                                           float* __restrict__ dw, int T, int h) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm_dw[];  // [h] CTA accumulators
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
@@ -354,16 +362,16 @@ static inline int grid_for(long long work_items, int per_block, int max_waves = 
 
 ODB_EXPORT int odb_embedding_fwd(const void* ids, const void* W, void* out, int T, int h, cudaStream_t st) {
   if (h % 8) return -1;
-  embedding_fwd_kernel<<<grid_for(T, 8), 256, 0, st>>>((const long long*)ids, (const __nv_bfloat16*)W,
-                                                       (__nv_bfloat16*)out, T, h);
+  launch_pdl(embedding_fwd_kernel, dim3(grid_for(T, 8)), dim3(256), 0, st, (const long long*)ids, (const __nv_bfloat16*)W,
+             (__nv_bfloat16*)out, T, h);
   ODB_CHECK_LAST();
   return 0;
 }
 
 ODB_EXPORT int odb_embedding_bwd(const void* ids, const void* dout, void* dW, int T, int h, float scale, cudaStream_t st) {
   if (h % 8) return -1;
-  embedding_bwd_kernel<<<grid_for(T, 8), 256, 0, st>>>((const long long*)ids, (const __nv_bfloat16*)dout, (float*)dW, T,
-                                                       h, scale);
+  launch_pdl(embedding_bwd_kernel, dim3(grid_for(T, 8)), dim3(256), 0, st, (const long long*)ids, (const __nv_bfloat16*)dout,
+             (float*)dW, T, h, scale);
   ODB_CHECK_LAST();
   return 0;
 }
@@ -384,10 +392,9 @@ ODB_EXPORT int odb_rmsnorm_fwd(const void* x_in, void* x_out, const void* delta,
                                int h, float eps, cudaStream_t st) {
   if (h % 8) return -1;
   const int grid = grid_for(T, 8, 4);
-  ODB_DISPATCH_NCH(h, (rmsnorm_fwd_kernel<NCH><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x_in, (__nv_bfloat16*)x_out,
-                                                                      (const __nv_bfloat16*)delta,
-                                                                      (const __nv_bfloat16*)w, (__nv_bfloat16*)y,
-                                                                      (float*)rstd, T, h, eps)));
+  ODB_DISPATCH_NCH(h, (launch_pdl(rmsnorm_fwd_kernel<NCH>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)x_in,
+                                  (__nv_bfloat16*)x_out, (const __nv_bfloat16*)delta, (const __nv_bfloat16*)w, (__nv_bfloat16*)y,
+                                  (float*)rstd, T, h, eps)));
   ODB_CHECK_LAST();
   return 0;
 }
@@ -397,9 +404,9 @@ ODB_EXPORT int odb_rmsnorm_bwd(const void* dy, const void* x, const void* w, con
   if (h % 8) return -1;
   const size_t smem = (size_t)h * sizeof(float);
   const int grid = grid_for(T, 8, 2);
-  ODB_DISPATCH_NCH(h, (rmsnorm_bwd_kernel<NCH, (NCH <= 8)><<<grid, 256, smem, st>>>(
-                          (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (const float*)rstd,
-                          (const __nv_bfloat16*)dres_in, (__nv_bfloat16*)dres_out, (float*)dw, T, h)));
+  ODB_DISPATCH_NCH(h, (launch_pdl(rmsnorm_bwd_kernel<NCH, (NCH <= 8)>, dim3(grid), dim3(256), smem, st,
+                                  (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (const float*)rstd,
+                                  (const __nv_bfloat16*)dres_in, (__nv_bfloat16*)dres_out, (float*)dw, T, h)));
   ODB_CHECK_LAST();
   return 0;
 }

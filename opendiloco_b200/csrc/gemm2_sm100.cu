@@ -137,6 +137,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   uint64_t* gu_full = tmem_empty + 2;                    // kSwiGLUBwd: [group][chunk] gate/up tiles landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gu_full + 4);
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();          // 0 = leader of the pair
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
@@ -157,6 +158,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   cluster_sync();          // barrier inits + TMEM allocation visible to the peer CTA
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();              // everything above touched only this CTA's shared / tensor memory
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -599,7 +601,7 @@ static int launch(const void* A, const void* B, void* C, void* aux, int M, int N
   const int tiles = p.num_m * p.num_n;
   const int max_clusters = sm_count() / 2;
   const int grid = 2 * (tiles < max_clusters ? tiles : max_clusters);
-  gemm2_bf16_tn_kernel<EPI, B_MN><<<grid, THREADS, smem, st>>>(ta, tb, tc, tx, ta1, ta2, p);    // cluster dims are compiled in (__cluster_dims__)
+  launch_pdl(gemm2_bf16_tn_kernel<EPI, B_MN>, dim3(grid), dim3(THREADS), smem, st, ta, tb, tc, tx, ta1, ta2, p);    // cluster dims are compiled in (__cluster_dims__)
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }

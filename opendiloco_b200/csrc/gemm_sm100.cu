@@ -65,6 +65,7 @@ template <int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_aux, Params p) {
+  pdl_launch_dependents();
   constexpr int STAGES = Cfg<EPI>::STAGES;
   constexpr int NBUF = Cfg<EPI>::NBUF;
   extern __shared__ uint8_t smem_raw[];
@@ -95,6 +96,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -306,7 +308,7 @@ static int launch(const void* A, const void* B, void* C, void* aux, int M, int N
   }
   const int tiles = p.num_m * p.num_n;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_bf16_tn_kernel<EPI><<<grid, THREADS, smem, st>>>(ta, tb, tc, tx, p);
+  launch_pdl(gemm_bf16_tn_kernel<EPI>, dim3(grid), dim3(THREADS), smem, st, ta, tb, tc, tx, p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }

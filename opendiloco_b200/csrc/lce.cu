@@ -219,6 +219,8 @@ constexpr float kLceShiftOffset = 40.f;
 __global__ void __launch_bounds__(1024) lce_prep_kernel(const long long* __restrict__ src, long long* __restrict__ dst, int B, int S,
                                                         float loss_scale, float* __restrict__ n_valid,
                                                         float* __restrict__ gscale, float* __restrict__ loss_sum) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sm[33];
   const int T = B * S;
   float cnt = 0.f;
@@ -241,6 +243,8 @@ __global__ void __launch_bounds__(256) lce_label_dot_kernel(const __nv_bfloat16*
                                                             const __nv_bfloat16* __restrict__ W, long long ldw,
                                                             const long long* __restrict__ labels, float* __restrict__ c,
                                                             int T, int h) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < T; t += gridDim.x * wpb) {
@@ -271,6 +275,8 @@ __global__ void __launch_bounds__(256) lce_finalize_kernel(const float* __restri
                                                            const __nv_bfloat16* __restrict__ x, long long ldx,
                                                            __nv_bfloat16* __restrict__ xs, long long ldxs,
                                                            float* __restrict__ dW, long long lddw, int h) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_part[4][LCE_FIN_ROWS];
   __shared__ float s_sq[4][LCE_FIN_ROWS];
   __shared__ float s_scale[LCE_FIN_ROWS];
@@ -334,8 +340,8 @@ __global__ void __launch_bounds__(256) lce_finalize_kernel(const float* __restri
 ODB_EXPORT int odb_lce_prep(const void* labels_in, void* labels_out, int B, int S, float loss_scale, void* n_valid, void* gscale,
                             void* loss_sum, cudaStream_t st) {
   if (B <= 0 || S <= 0) return -1;
-  lce_prep_kernel<<<1, 1024, 0, st>>>((const long long*)labels_in, (long long*)labels_out, B, S, loss_scale, (float*)n_valid,
-                                      (float*)gscale, (float*)loss_sum);
+  launch_pdl(lce_prep_kernel, dim3(1), dim3(1024), 0, st, (const long long*)labels_in, (long long*)labels_out, B, S, loss_scale,
+             (float*)n_valid, (float*)gscale, (float*)loss_sum);
   ODB_CHECK_LAST();
   return 0;
 }
@@ -344,8 +350,8 @@ ODB_EXPORT int odb_lce_label_dot(const void* x, long long ldx, const void* W, lo
                                  int h, cudaStream_t st) {
   if (h % 8 || ldx % 8 || ldw % 8) return -1;
   const int blocks = ceil_div(T, 8) < 148 * 8 ? ceil_div(T, 8) : 148 * 8;
-  lce_label_dot_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)W, ldw,
-                                               (const long long*)labels, (float*)c, T, h);
+  launch_pdl(lce_label_dot_kernel, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)W, ldw,
+             (const long long*)labels, (float*)c, T, h);
   ODB_CHECK_LAST();
   return 0;
 }
@@ -355,10 +361,9 @@ ODB_EXPORT int odb_lce_finalize(const void* partials, int planes, int T, const v
                                 void* sumsq, void* rowscale, const void* x, long long ldx, void* xs, long long ldxs, void* dW,
                                 long long lddw, int h, cudaStream_t st) {
   if (h % 8 || ldx % 8 || ldxs % 8 || lddw % 4) return -1;
-  lce_finalize_kernel<<<ceil_div(T, LCE_FIN_ROWS), 256, 0, st>>>((const float*)partials, planes, T, (const long long*)labels,
-                                                                 (const float*)gscale, (float*)loss_sum, (float*)sumsq,
-                                                                 (float*)rowscale, (const __nv_bfloat16*)x, ldx,
-                                                                 (__nv_bfloat16*)xs, ldxs, (float*)dW, lddw, h);
+  launch_pdl(lce_finalize_kernel, dim3(ceil_div(T, LCE_FIN_ROWS)), dim3(256), 0, st, (const float*)partials, planes, T,
+             (const long long*)labels, (const float*)gscale, (float*)loss_sum, (float*)sumsq, (float*)rowscale,
+             (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)xs, ldxs, (float*)dW, lddw, h);
   ODB_CHECK_LAST();
   return 0;
 }

@@ -65,6 +65,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
@@ -84,6 +85,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
   cluster_sync();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   // work item -> (token slice, tile): pairs running at the same time work on DIFFERENT output tiles of the SAME token
   // slice, so they share dY / X tiles in L2 and never reduce-add into the same addresses at the same moment
@@ -258,7 +260,7 @@ ODB_EXPORT int odb_wgrad_bf16(const void* dY0, const void* dY1, const void* dY2,
   }
   const int work = tiles * p.splits;
   const int grid = 2 * (work < pairs ? work : pairs);
-  wgrad_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(ta0, ta1, ta2, tb, tc, p);
+  launch_pdl(wgrad_kernel, dim3(grid), dim3(THREADS), SMEM_BYTES, st, ta0, ta1, ta2, tb, tc, p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }
