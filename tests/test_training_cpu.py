@@ -214,3 +214,35 @@ def test_run_training_sh_launches_two_workers(tmp_path):
     assert "Training completed." in logs[0] and "Training completed." in logs[1]
     assert "DiLoCo enabled: 2 workers x 1 GPU(s)" in logs[0]
     assert set(_load(f"{tmp_path}/log.pkl")) == {1, 2, 3, 4}
+
+
+def test_checkpoint_interchange_with_the_dcp_format(tmp_path):
+    """Our flat-shard checkpoint -> the reference's DCP layout (ckpt_utils.py:48-100: dcp.save of {"model", "optimizer"} +
+    global_state_dict.pt) -> back: weights, Adam moments, step, outer momentum survive the round trip, and the DCP directory
+    loads with plain ``dcp.load`` into HF-named tensors."""
+    import torch
+    import torch.distributed.checkpoint as dcp
+
+    from opendiloco_b200.models.config import LlamaConfig
+    from opendiloco_b200.utils.ckpt import _load
+    from opendiloco_b200.utils.dcp_interop import export_dcp, import_dcp
+
+    ckpt = f"{tmp_path}/ckpt"
+    hv = ["--hv.local_steps", "2", "--hv.galaxy_size", "2", "--hv.skip_load_from_peers", "--hv.matchmaking_time", "1",
+          "--total_batch_size", "8", "--max_steps", "4"]
+    torchrun(2, "opendiloco_b200.train_fsdp", BASE + hv + ["--ckpt.path", ckpt, "--ckpt.interval", "4", "--project", f"{tmp_path}/l.pkl"])
+    src = f"{ckpt}/model_step_4/diloco_rank_0"
+    export_dcp(src, f"{tmp_path}/dcp")
+    assert os.path.isfile(f"{tmp_path}/dcp/.metadata") and os.path.isfile(f"{tmp_path}/dcp/global_state_dict.pt")
+    cfg = LlamaConfig.from_pretrained("2m")
+    name = "model.layers.1.mlp.down_proj.weight"
+    probe = {"model": {name: torch.zeros(cfg.hidden_size, cfg.intermediate_size)}}
+    dcp.load(probe, checkpoint_id=f"{tmp_path}/dcp", no_dist=True)
+    assert probe["model"][name].abs().sum() > 0
+    g = _load(f"{tmp_path}/dcp/global_state_dict.pt")
+    assert g["outer_optimizer"]["state"][0]["momentum_buffer"].shape == (cfg.vocab_size, cfg.hidden_size)
+    import_dcp(f"{tmp_path}/dcp", f"{tmp_path}/back", cfg)
+    a, b = _load(f"{src}/__0_0.distcp"), _load(f"{tmp_path}/back/__0_0.distcp")
+    for key in ("model", "exp_avg", "exp_avg_sq", "outer_momentum"):
+        assert torch.equal(a[key].float(), b[key].float()), key
+    assert a["step"] == b["step"] == 4
