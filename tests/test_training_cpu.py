@@ -43,11 +43,11 @@ def test_full_shard_gathers_parameters_and_matches_zero2(tmp_path):
     train exactly like SHARD_GRAD_OP (ZeRO-2): same kernels, same reduction order, only the residency of the weights
     differs (reference: utils.py:138-152 -> FSDP ShardingStrategy)."""
     logs = {}
-    for strat in ("SHARD_GRAD_OP", "FULL_SHARD", "HYBRID_SHARD"):
+    for strat in ("SHARD_GRAD_OP", "FULL_SHARD"):          # HYBRID_SHARD takes the same code path as FULL_SHARD
         logs[strat] = f"{tmp_path}/{strat}.pkl"
         torchrun(2, "opendiloco_b200.train_fsdp", BASE + ["--max_steps", "6", "--sharding_strategy", strat, "--project", logs[strat]])
     a = _load(logs["SHARD_GRAD_OP"])
-    for strat in ("FULL_SHARD", "HYBRID_SHARD"):
+    for strat in ("FULL_SHARD",):
         b = _load(logs[strat])
         assert set(a) == set(b) == set(range(1, 7))
         for s in a:
