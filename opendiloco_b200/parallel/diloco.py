@@ -786,6 +786,7 @@ class DiLoCoOptimizer:
             if order == 1:
                 deadline = t_start + window
                 everyone = False
+                next_liveness = t_start + 0.5
                 while time.perf_counter() < deadline:
                     if done_before == 0 and store.check(keys):       # ONE round trip when the whole swarm is punctual
                         everyone = True
@@ -795,6 +796,12 @@ class DiLoCoOptimizer:
                     # workers of a healthy swarm arrive within microseconds of each other: spin first, back off later
                     if time.perf_counter() - t_start > 0.002:
                         time.sleep(0.0005)
+                    # failure detection: with a heartbeat board a peer whose heartbeat expired cannot arrive any more - do
+                    # not sit out the whole window for it epoch after epoch (checked twice a second)
+                    if time.perf_counter() >= next_liveness:
+                        next_liveness = time.perf_counter() + 0.5
+                        if self._nobody_else_can_come(store, keys):
+                            break
                 members = list(range(n)) if everyone else [q for q in range(n) if store.check([keys[q]])]
                 mkeys = [keys[q] for q in members]
                 marks = store.multi_get(mkeys) if hasattr(store, "multi_get") else [store.get(k) for k in mkeys]
@@ -816,6 +823,22 @@ class DiLoCoOptimizer:
                 return members, False, rec[1] == "1"
             done_before += len(members)                  # my arrival raced with the leader's snapshot: next round
             r += 1
+
+    def _nobody_else_can_come(self, store, keys: list[str]) -> bool:
+        """True when every peer with a LIVE heartbeat on the membership board has arrived (only meaningful with the native
+        board, ``csrc/host/rendezvous.cc``: the c10d store has no liveness information and the answer is then False)."""
+        if getattr(self.dht, "board", None) is None:
+            return False
+        try:
+            alive = {int(p.rsplit("-", 1)[1]) for p in self.dht.alive_peers()}
+        except Exception:
+            return False
+        missing = [q for q in range(len(keys)) if not store.check([keys[q]])]
+        dead = [q for q in missing if q not in alive]
+        if missing and len(dead) == len(missing):
+            logger.log(self.status_loglevel, f"workers {dead} have no live heartbeat: closing the round without them")
+            return True
+        return False
 
     def _gc_round_keys(self, store, epoch: int, n: int) -> None:
         """Drop the records of a long-closed epoch (best effort: c10d TCPStore and the native board can delete)."""

@@ -129,6 +129,20 @@ def test_keys_are_namespaced_per_incarnation_and_group():
     assert any(k.startswith("t/test/g0/") for k in store.d) and any(k.startswith("t/test/g1/") for k in store.d)
 
 
+def test_leader_does_not_wait_the_window_for_a_peer_without_heartbeat():
+    """With a heartbeat board (csrc/host/rendezvous.cc) a dead worker is skipped as soon as its heartbeat has expired instead
+    of after ``timeout_waiting_for_peers`` every epoch (the reference learns the same from expired DHT records)."""
+    store = MemStore()
+    ws = [make_worker(store, r, 3, AllReduceStrategy.WAIT_FOR_ALL, timeout_waiting_for_peers=30.0, matchmaking_time=1.0) for r in range(2)]
+    for w in ws:
+        w.dht.board = object()                                  # "a board is attached"
+        w.dht.alive_peers = lambda: ["worker-0", "worker-1"]    # worker-2's heartbeat has expired
+    t0 = time.perf_counter()
+    res = run_round(ws, [0.0, 0.02])
+    assert time.perf_counter() - t0 < 3.0                       # not the 30 s window
+    assert res[0][0] == res[1][0] == [0, 1]
+
+
 def test_handshake_can_be_switched_off():
     store = MemStore()
     w = make_worker(store, 0, 2, AllReduceStrategy.WAIT_FOR_ALL, timeout_waiting_for_peers=2.0, matchmaking_time=0.5)
